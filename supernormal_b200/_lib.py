@@ -1,0 +1,96 @@
+"""ctypes binding of libsnb200.so (the C ABI declared in include/snb200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or an entry point returns an
+error the call raises.  Prototypes are parsed from the header itself so the Python side cannot
+drift from the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, List, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(_HERE, "..", "include", "snb200.h")
+LIB_PATH = os.path.join(_HERE, "lib", "libsnb200.so")
+
+SNB_MAX_LEVELS = 16
+
+
+class HashGridMeta(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("offsets", C.c_uint32 * (SNB_MAX_LEVELS + 1)),
+                ("scales", C.c_float * SNB_MAX_LEVELS), ("resolutions", C.c_uint32 * SNB_MAX_LEVELS)]
+
+
+_CTYPE = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "float": C.c_float,
+          "snb_stream_t": C.c_void_p}
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
+    """{symbol: (restype, [argtypes])} for every `snb_*` function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(const char \*|int32_t|uint32_t)\s*(snb_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        argtypes = []
+        for a in [s.strip() for s in args.split(",")]:
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                argtypes.append(C.c_void_p)
+            else:
+                argtypes.append(_CTYPE[a.split()[-2] if a.split()[0] != "const" else a.split()[1]])
+        restype = C.c_char_p if "char" in ret else _CTYPE[ret]
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m supernormal_b200.build` "
+                "(nvcc, sm_100a). supernormal_b200 has no CPU or PyTorch fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in parse_header().items():
+            fn = getattr(_lib, name)  # AttributeError if the header and the .so disagree
+            fn.restype, fn.argtypes = restype, argtypes
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError(f"libsnb200 error {rc}: {lib().snb_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL). The tensor must be CUDA + contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NotImplementedError("Only support cuda inputs.")  # nerfacc's own message, NA/ray_marching.py:131
+    assert t.is_contiguous(), "libsnb200 needs contiguous tensors"
+    return t.data_ptr() or None
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args, stream()))
+
+
+def make_meta(n_levels, log2_hashmap_size, base_resolution, per_level_scale) -> Tuple[HashGridMeta, int]:
+    m = HashGridMeta()
+    total = lib().snb_hashgrid_make_meta(n_levels, log2_hashmap_size, base_resolution, per_level_scale, C.byref(m))
+    if total == 0:
+        raise RuntimeError(lib().snb_last_error().decode())
+    return m, int(total)

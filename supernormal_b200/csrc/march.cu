@@ -1,0 +1,225 @@
+// march.cu -- occupancy-grid ray marching, warp-per-ray, bit-exact with the reference kernel
+// (CS/ray_marching.cu:81-192 as compiled by nvcc for sm_100a; rounding recipe in SURVEY.md
+// Appendix C).  Every floating-point operation is an explicit round-to-nearest intrinsic so the
+// result does not depend on this translation unit's contraction decisions.
+//
+// Parallelisation: the reference runs one thread per ray and walks it serially.  Here a warp owns
+// the ray.  Lane l replays the (cheap, serial) t0/t1 recurrence l steps ahead, all 32 lanes fetch
+// their occupancy byte concurrently (one L2 round trip per 32 candidate samples instead of 32),
+// a ballot finds the first candidate that is not an occupied in-range sample, and the occupied
+// prefix is stored with one coalesced write.  Only the empty-space skip (whose repeated
+// `t += dt` must be replayed add-by-add to stay bit-exact) is serial.
+#include "common.cuh"
+
+namespace snb {
+
+struct MarchArgs {
+    int32_t n_rays;
+    const float *rays_o, *rays_d, *t_min, *t_max, *roi;
+    int3 res;
+    const uint8_t *grid;
+    float step, cone;
+};
+
+__device__ __forceinline__ float calc_dt(float t, float cone, float dt_min) {
+    // clamp(t*cone, dt_min, 1e10) == fmaxf(dt_min, fminf(t*cone, 1e10))  (helpers_math.h:1167)
+    return fmaxf(dt_min, fminf(__fmul_rn(t, cone), 1e10f));
+}
+
+__device__ __forceinline__ bool occupied_at(float x, float y, float z, const float *roi_min, const float *roi_max,
+                                            int3 res, const uint8_t *__restrict__ grid) {
+    if (x < roi_min[0] || x > roi_max[0] || y < roi_min[1] || y > roi_max[1] || z < roi_min[2] || z > roi_max[2])
+        return false;
+    float ux = __fdiv_rn(__fsub_rn(x, roi_min[0]), __fsub_rn(roi_max[0], roi_min[0]));
+    float uy = __fdiv_rn(__fsub_rn(y, roi_min[1]), __fsub_rn(roi_max[1], roi_min[1]));
+    float uz = __fdiv_rn(__fsub_rn(z, roi_min[2]), __fsub_rn(roi_max[2], roi_min[2]));
+    int ix = min(max(__float2int_rz(__fmul_rn(ux, (float)res.x)), 0), res.x - 1);
+    int iy = min(max(__float2int_rz(__fmul_rn(uy, (float)res.y)), 0), res.y - 1);
+    int iz = min(max(__float2int_rz(__fmul_rn(uz, (float)res.z)), 0), res.z - 1);
+    return __ldg(grid + ((ix * res.y + iy) * res.z + iz)) != 0;
+}
+
+__device__ __forceinline__ float axis_dist(float p, float dir, float inv_dir, float rmin, float rmax, int r) {
+    // ((floorf(_x + 0.5 + 0.5*sign(dir)) - _x) * inv_dir) / res * (roi_max-roi_min), _x = u*res
+    float rf = (float)r;
+    float ext = __fsub_rn(rmax, rmin);
+    float u = __fdiv_rn(__fsub_rn(p, rmin), ext);
+    float fl = floorf(__fmaf_rn(copysignf(1.0f, dir), 0.5f, __fmaf_rn(rf, u, 0.5f)));
+    float diff = __fmaf_rn(rf, -u, fl);
+    return __fmul_rn(__fdiv_rn(__fmul_rn(diff, inv_dir), rf), ext);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *__restrict__ packed_info,
+                                                    int64_t capacity, int32_t *__restrict__ num_steps,
+                                                    int64_t *__restrict__ ridx64, int32_t *__restrict__ ridx32,
+                                                    float *__restrict__ t_starts, float *__restrict__ t_ends) {
+    const int lane = threadIdx.x & 31;
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= a.n_rays) return;
+
+    const float ox = __ldg(a.rays_o + 3 * ray), oy = __ldg(a.rays_o + 3 * ray + 1), oz = __ldg(a.rays_o + 3 * ray + 2);
+    const float dx = __ldg(a.rays_d + 3 * ray), dy = __ldg(a.rays_d + 3 * ray + 1), dz = __ldg(a.rays_d + 3 * ray + 2);
+    const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+    const float near = __ldg(a.t_min + ray), far = __ldg(a.t_max + ray);
+    float rmin[3] = {__ldg(a.roi), __ldg(a.roi + 1), __ldg(a.roi + 2)};
+    float rmax[3] = {__ldg(a.roi + 3), __ldg(a.roi + 4), __ldg(a.roi + 5)};
+    const float dt_min = a.step;
+
+    int64_t base = 0;
+    if (EMIT) base = packed_info[2 * ray];
+
+    int j = 0;
+    float t0 = near;
+    float t1 = __fadd_rn(t0, calc_dt(t0, a.cone, dt_min));
+    float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+
+    while (t_mid < far) {  // warp-uniform state
+        // lane l: state after l consecutive occupied samples
+        float l0 = t0, l1 = t1;
+        for (int s = 0; s < lane; ++s) {
+            l0 = l1;
+            l1 = __fadd_rn(l0, calc_dt(l0, a.cone, dt_min));
+        }
+        float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
+        float px = __fmaf_rn(lm, dx, ox), py = __fmaf_rn(lm, dy, oy), pz = __fmaf_rn(lm, dz, oz);
+        bool in_range = lm < far;
+        bool occ = in_range && occupied_at(px, py, pz, rmin, rmax, a.res, a.grid);
+        unsigned stop = ~__ballot_sync(0xffffffffu, occ);
+        int f = stop ? (__ffs(stop) - 1) : 32;  // lanes [0,f) are emitted samples
+        if (EMIT && lane < f) {
+            int64_t o = base + j + lane;
+            if (o < capacity) {
+                t_starts[o] = l0;
+                t_ends[o] = l1;
+                if (ridx64) ridx64[o] = ray;
+                if (ridx32) ridx32[o] = ray;
+            }
+        }
+        j += f;
+        if (f == 32) {  // continue after lane 31's sample
+            float n0 = __shfl_sync(0xffffffffu, l1, 31);
+            t0 = n0;
+            t1 = __fadd_rn(t0, calc_dt(t0, a.cone, dt_min));
+            t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+            continue;
+        }
+        // state of the first non-sample candidate
+        float s_mid = __shfl_sync(0xffffffffu, lm, f);
+        bool s_in = __shfl_sync(0xffffffffu, (int)in_range, f) != 0;
+        if (!s_in) break;  // t_mid >= far (or NaN): the reference loop exits here
+        float sx = __shfl_sync(0xffffffffu, px, f), sy = __shfl_sync(0xffffffffu, py, f), sz = __shfl_sync(0xffffffffu, pz, f);
+        // advance_to_next_voxel (CS/ray_marching.cu:59-75)
+        float tx = axis_dist(sx, dx, ix, rmin[0], rmax[0], a.res.x);
+        float ty = axis_dist(sy, dy, iy, rmin[1], rmax[1], a.res.y);
+        float tz = axis_dist(sz, dz, iz, rmin[2], rmax[2], a.res.z);
+        float dist = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+        float t_target = fminf(__fadd_rn(s_mid, dist), far);
+        float t = s_mid;
+        do {
+            t = __fadd_rn(t, dt_min);
+        } while (t < t_target);
+        t_mid = t;
+        float dt = calc_dt(t_mid, a.cone, dt_min);
+        t0 = __fmaf_rn(dt, -0.5f, t_mid);
+        t1 = __fmaf_rn(dt, 0.5f, t_mid);
+    }
+    if (!EMIT && lane == 0) num_steps[ray] = j;
+}
+
+// Exclusive scan of per-ray counts in one CTA (n is a few thousand on the training path; the loop
+// handles any n).  packed_info[i] = (offset_i, count_i); *total = sum.
+__global__ void __launch_bounds__(1024) packed_info_kernel(int32_t n, const int32_t *__restrict__ counts,
+                                                           int32_t *__restrict__ packed, int32_t *__restrict__ total) {
+    __shared__ int32_t warp_sums[32];
+    __shared__ int32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int32_t start = 0; start < n; start += 1024) {
+        int32_t i = start + threadIdx.x;
+        int32_t c = (i < n) ? counts[i] : 0;
+        int32_t v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) warp_sums[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        int32_t carry = carry_s;
+        int32_t incl = v + (warp ? warp_sums[warp - 1] : 0) + carry;
+        if (i < n) {
+            packed[2 * i] = incl - c;
+            packed[2 * i + 1] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+static int32_t check_march(int32_t n_rays, const void *o, const void *d, const void *tmin, const void *tmax,
+                           const void *roi, int rx, int ry, int rz, const void *grid, float step) {
+    SNB_REQUIRE(n_rays >= 0, SNB_ERR_ARG, "ray_marching: n_rays < 0");
+    SNB_REQUIRE(n_rays == 0 || (o && d && tmin && tmax), SNB_ERR_NULL, "ray_marching: null ray buffer");
+    SNB_REQUIRE(roi && grid, SNB_ERR_NULL, "ray_marching: null roi/grid");
+    SNB_REQUIRE(step > 0.0f, SNB_ERR_ARG, "ray_marching: step_size must be > 0");
+    SNB_REQUIRE(rx > 0 && ry > 0 && rz > 0 && (int64_t)rx * ry * rz < (1ll << 31), SNB_ERR_ARG,
+                "ray_marching: bad grid resolution %d %d %d", rx, ry, rz);
+    return SNB_OK;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int32_t snb_march_count(int32_t n_rays, const float *rays_o, const float *rays_d, const float *t_min,
+                                   const float *t_max, const float *roi, int32_t res_x, int32_t res_y, int32_t res_z,
+                                   const uint8_t *grid_binary, float step_size, float cone_angle, int32_t *num_steps,
+                                   snb_stream_t stream) {
+    int32_t rc = check_march(n_rays, rays_o, rays_d, t_min, t_max, roi, res_x, res_y, res_z, grid_binary, step_size);
+    if (rc) return rc;
+    if (n_rays == 0) return SNB_OK;
+    SNB_REQUIRE(num_steps, SNB_ERR_NULL, "march_count: null num_steps");
+    MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, make_int3(res_x, res_y, res_z), grid_binary, step_size, cone_angle};
+    march_kernel<false><<<(unsigned)cdiv(n_rays, 4), 128, 0, S(stream)>>>(a, nullptr, 0, num_steps, nullptr, nullptr, nullptr, nullptr);
+    SNB_LAUNCH_CHECK("march_count");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_packed_info_from_counts(int32_t n_rays, const int32_t *num_steps, int32_t *packed_info,
+                                               int32_t *total, snb_stream_t stream) {
+    SNB_REQUIRE(n_rays >= 0, SNB_ERR_ARG, "packed_info: n_rays < 0");
+    SNB_REQUIRE(n_rays == 0 || (num_steps && packed_info), SNB_ERR_NULL, "packed_info: null buffer");
+    packed_info_kernel<<<1, 1024, 0, S(stream)>>>(n_rays, num_steps, packed_info, total);
+    SNB_LAUNCH_CHECK("packed_info");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_march_emit(int32_t n_rays, const float *rays_o, const float *rays_d, const float *t_min,
+                                  const float *t_max, const float *roi, int32_t res_x, int32_t res_y, int32_t res_z,
+                                  const uint8_t *grid_binary, float step_size, float cone_angle,
+                                  const int32_t *packed_info, int64_t capacity, int64_t *ray_indices_i64,
+                                  int32_t *ray_indices_i32, float *t_starts, float *t_ends, snb_stream_t stream) {
+    int32_t rc = check_march(n_rays, rays_o, rays_d, t_min, t_max, roi, res_x, res_y, res_z, grid_binary, step_size);
+    if (rc) return rc;
+    if (n_rays == 0 || capacity == 0) return SNB_OK;
+    SNB_REQUIRE(packed_info && t_starts && t_ends, SNB_ERR_NULL, "march_emit: null output");
+    MarchArgs a{n_rays, rays_o, rays_d, t_min, t_max, roi, make_int3(res_x, res_y, res_z), grid_binary, step_size, cone_angle};
+    march_kernel<true><<<(unsigned)cdiv(n_rays, 4), 128, 0, S(stream)>>>(a, packed_info, capacity, nullptr, ray_indices_i64,
+                                                                        ray_indices_i32, t_starts, t_ends);
+    SNB_LAUNCH_CHECK("march_emit");
+    return SNB_OK;
+}

@@ -1,0 +1,42 @@
+"""CPU: the C-ABI library loads and exports every symbol include/snb200.h declares (no compute calls)."""
+import ctypes
+import os
+import subprocess
+
+from supernormal_b200 import _lib, build
+
+
+def test_header_symbols_exported():
+    path = build.build_library()
+    assert os.path.exists(path)
+    protos = _lib.parse_header()
+    assert len(protos) >= 20 and "snb_march_emit" in protos and "snb_hashgrid_bwd_bwd_input" in protos
+    so = ctypes.CDLL(path)
+    missing = [n for n in protos if not hasattr(so, n)]
+    assert not missing, missing
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", path], text=True)
+    undeclared = [l.split()[-1] for l in exported.splitlines() if " T snb_" in l and l.split()[-1] not in protos]
+    assert not undeclared, f"exported but not in the header: {undeclared}"
+
+
+def test_host_only_entry_points():
+    l = _lib.lib()
+    assert l.snb_version() >= 100
+    m, total = _lib.make_meta(14, 19, 32, 1.3195079107728942)
+    assert total == 5936000 and list(m.resolutions)[:4] == [32, 43, 56, 74]
+    import oracle
+    s = oracle.hashgrid_spec()
+    assert list(m.offsets)[:15] == s.offsets.tolist() and list(m.scales)[:14] == s.scales.tolist()
+    # argument errors are reported, not crashed on
+    assert l.snb_hashgrid_make_meta(99, 19, 32, 1.5, ctypes.byref(m)) == 0
+    assert b"n_levels" in l.snb_last_error()
+    assert l.snb_march_count(-1, None, None, None, None, None, 1, 1, 1, None, 0.1, 0.0, None, None) == -2
+
+
+def test_product_has_no_oracle_import():
+    root = os.path.dirname(os.path.abspath(_lib.__file__))
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

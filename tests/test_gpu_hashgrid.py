@@ -1,0 +1,125 @@
+"""GPU parity: tcnn-shaped Encoding (forward bit-exact vs the fp16-faithful C oracle; gradients vs
+exact double-precision oracles, tolerances stated)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import torch_ops as T
+
+pytestmark = pytest.mark.gpu
+
+CFGS = {
+    "small": dict(otype="HashGrid", n_levels=6, n_features_per_level=2, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.7),
+    "diligent": dict(otype="HashGrid", n_levels=14, n_features_per_level=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=1.3195079107728942),
+    "l16": dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=1.3195079107728942),
+}
+
+
+def _enc(cfg, cuda, scale=1.0, dtype=None, seed=0):
+    from supernormal_b200 import tcnn_api as tcnn
+    enc = tcnn.Encoding(3, cfg, dtype=dtype).to(cuda)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        enc.params.copy_(((torch.rand(enc.params.numel(), generator=g) * 2 - 1) * scale).to(cuda))
+    return enc
+
+
+@pytest.mark.parametrize("name,scale,n", [("small", 1.0, 4099), ("diligent", 1e-4, 3000), ("diligent", 0.5, 3000), ("l16", 0.1, 2000)])
+def test_forward_bit_exact(cuda, name, scale, n):
+    cfg = CFGS[name]
+    enc = _enc(cfg, cuda, scale)
+    spec = oracle.hashgrid_spec(**cfg)
+    assert enc.n_output_dims == spec.n_output_dims and enc.params.numel() == spec.n_params
+    rng = np.random.RandomState(1)
+    x = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)   # the reference feeds [-1,1], not [0,1] (models/fields.py:78)
+    x[:8] = [[0, 0, 0], [1, 1, 1], [-1, -1, -1], [0.5, -0.5, 0.25], [1, -1, 0], [-0.999999, 0.3, 0.7], [0.0322581, 0.0967742, 0.16129], [1e-8, -1e-8, 0]]
+    out = enc(torch.from_numpy(x).to(cuda))
+    assert out.dtype == torch.float16 and out.shape == (n, spec.n_output_dims)
+    ref = oracle.hashgrid_fwd(spec, x, enc.params.detach().cpu().numpy().astype(np.float16))
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), ref.view(np.uint16))
+    # level masking extension == zeroed features (models/fields.py:81-83)
+    enc.n_active_levels = 3
+    out3 = enc(torch.from_numpy(x).to(cuda))
+    ref3 = oracle.hashgrid_fwd(spec, x, enc.params.detach().cpu().numpy().astype(np.float16), n_active=3)
+    assert np.array_equal(out3.cpu().numpy().view(np.uint16), ref3.view(np.uint16)) and (out3[:, 6:] == 0).all()
+
+
+def test_forward_sizes_and_errors(cuda):
+    enc = _enc(CFGS["small"], cuda)
+    assert enc(torch.zeros(0, 3, device=cuda)).shape == (0, 12)
+    assert enc(torch.rand(1, 3, device=cuda)).shape == (1, 12)   # any N: no batch-granularity padding needed
+    with pytest.raises(NotImplementedError):
+        enc(torch.rand(4, 3))
+    assert [k for k, _ in enc.named_parameters()] == ["params"] and enc.params.dtype == torch.float32
+    enc32 = _enc(CFGS["small"], cuda, dtype=torch.float32)
+    x = torch.rand(100, 3, device=cuda) * 2 - 1
+    assert torch.equal(enc32(x), enc(x).float())
+    # the fp16 shadow table follows in-place parameter updates (optimizer steps)
+    before = enc(x).clone()
+    with torch.no_grad():
+        enc.params.mul_(2.0)
+    assert torch.allclose(enc(x).float(), before.float() * 2, rtol=2e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["small", "diligent"])
+def test_backward_table_and_input(cuda, name):
+    cfg = CFGS[name]
+    enc = _enc(cfg, cuda, 0.3, dtype=torch.float32)
+    spec = oracle.hashgrid_spec(**cfg)
+    rng = np.random.RandomState(2)
+    n = 2500
+    x = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    dy = rng.normal(size=(n, spec.n_output_dims)).astype(np.float32)
+    xt = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    out = enc(xt)
+    out.backward(torch.from_numpy(dy).to(cuda))
+    g_ref = oracle.hashgrid_bwd_table(spec, x, dy)
+    # fp32 atomics vs exact: relative 1e-5 of the largest entry
+    assert np.abs(enc.params.grad.cpu().numpy() - g_ref).max() <= 1e-5 * max(1.0, np.abs(g_ref).max())
+    # input gradient vs double-precision autograd through the ATen-op oracle (table rounded to fp16 in both)
+    p64 = enc.params.detach().cpu().half().double()
+    x64 = torch.from_numpy(x).double().requires_grad_(True)
+    o64 = T.hashgrid_encode(x64, p64, spec, fp16=False)
+    (gx,) = torch.autograd.grad(o64, x64, torch.from_numpy(dy).double())
+    # positions are cast fp32->fp64 so cell/weights agree to ~1e-7; scale up to 1175 amplifies: rel 2e-4
+    err = (xt.grad.cpu().double() - gx).abs().max().item()
+    assert err <= 2e-4 * gx.abs().max().item(), err
+
+
+def test_double_backward(cuda):
+    """d/d{params, dout, x} of <dL_dx, v>: what SDFNetwork.gradient(create_graph=True) + loss.backward() exercises."""
+    cfg = CFGS["small"]
+    enc = _enc(cfg, cuda, 0.5, dtype=torch.float32)
+    spec = oracle.hashgrid_spec(**cfg)
+    rng = np.random.RandomState(3)
+    n = 1500
+    x = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    dy = rng.normal(size=(n, spec.n_output_dims)).astype(np.float32)
+    v = rng.normal(size=(n, 3)).astype(np.float32)
+    xt = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    dyt = torch.from_numpy(dy).to(cuda).requires_grad_(True)
+    (gx,) = torch.autograd.grad(enc(xt), xt, dyt, create_graph=True)
+    gp, gdy, gx2 = torch.autograd.grad((gx * torch.from_numpy(v).to(cuda)).sum(), [enc.params, dyt, xt])
+    p64 = enc.params.detach().cpu().half().double().requires_grad_(True)
+    x64 = torch.from_numpy(x).double().requires_grad_(True)
+    dy64 = torch.from_numpy(dy).double().requires_grad_(True)
+    (gx64,) = torch.autograd.grad(T.hashgrid_encode(x64, p64, spec, fp16=False), x64, dy64, create_graph=True)
+    rp, rdy, rx2 = torch.autograd.grad((gx64 * torch.from_numpy(v).double()).sum(), [p64, dy64, x64])
+    for got, ref, tol in ((gp, rp, 2e-4), (gdy, rdy, 2e-4), (gx2, rx2, 5e-4)):
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= tol * max(ref.abs().max().item(), 1e-6), (err, ref.abs().max().item())
+
+
+def test_sdf_network_gradient_path(cuda):
+    """models/fields.py:107-119 pattern end-to-end through torch autograd with the CUDA encoding."""
+    from supernormal_b200 import tcnn_api as tcnn
+    cfg = CFGS["small"]
+    enc = _enc(cfg, cuda, 0.5)
+    lin = torch.nn.Linear(3 + enc.n_output_dims, 1).to(cuda)
+    x = (torch.rand(512, 3, device=cuda) * 2 - 1).requires_grad_(True)
+    y = lin(torch.cat([x, enc(x).to(torch.float32)], 1))
+    (g,) = torch.autograd.grad(y, x, torch.ones_like(y), create_graph=True)
+    loss = ((g.norm(dim=-1) - 1) ** 2).mean()
+    loss.backward()
+    assert enc.params.grad is not None and torch.isfinite(enc.params.grad).all() and enc.params.grad.abs().sum() > 0
