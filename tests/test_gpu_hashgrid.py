@@ -37,12 +37,12 @@ def test_forward_bit_exact(cuda, name, scale, n):
     out = enc(torch.from_numpy(x).to(cuda))
     assert out.dtype == torch.float16 and out.shape == (n, spec.n_output_dims)
     ref = oracle.hashgrid_fwd(spec, x, enc.params.detach().cpu().numpy().astype(np.float16))
-    assert np.array_equal(out.cpu().numpy().view(np.uint16), ref.view(np.uint16))
+    assert np.array_equal(out.detach().cpu().numpy().view(np.uint16), ref.view(np.uint16))
     # level masking extension == zeroed features (models/fields.py:81-83)
     enc.n_active_levels = 3
     out3 = enc(torch.from_numpy(x).to(cuda))
     ref3 = oracle.hashgrid_fwd(spec, x, enc.params.detach().cpu().numpy().astype(np.float16), n_active=3)
-    assert np.array_equal(out3.cpu().numpy().view(np.uint16), ref3.view(np.uint16)) and (out3[:, 6:] == 0).all()
+    assert np.array_equal(out3.detach().cpu().numpy().view(np.uint16), ref3.view(np.uint16)) and (out3[:, 6:] == 0).all()
 
 
 def test_forward_sizes_and_errors(cuda):
@@ -83,7 +83,13 @@ def test_backward_table_and_input(cuda, name):
     o64 = T.hashgrid_encode(x64, p64, spec, fp16=False)
     (gx,) = torch.autograd.grad(o64, x64, torch.from_numpy(dy).double())
     # positions are cast fp32->fp64 so cell/weights agree to ~1e-7; scale up to 1175 amplifies: rel 2e-4
-    err = (xt.grad.cpu().double() - gx).abs().max().item()
+    # dy/dx is piecewise constant: a point within fp32 rounding of a cell face may land in the neighbouring
+    # cell in fp64 -- exclude those (measure-zero set) from the comparison
+    pos = x[:, None, :].astype(np.float64) * spec.scales[None, :, None].astype(np.float64) + 0.5
+    frac = pos - np.floor(pos)
+    safe = torch.from_numpy((np.minimum(frac, 1 - frac) > 1e-4).all(axis=(1, 2)))
+    assert safe.float().mean() > 0.9
+    err = (xt.grad.cpu().double() - gx)[safe].abs().max().item()
     assert err <= 2e-4 * gx.abs().max().item(), err
 
 
