@@ -138,6 +138,104 @@ int32_t snb_hashgrid_bwd_bwd_input(int64_t n, const float *x, const float *g2, c
                                    uint32_t n_active, float *table_grad, float *d_dL_dy, float *dx2,
                                    snb_stream_t stream);
 
+
+/* =======================================================================================
+ * Fused training path: the same operators as above, fused so that one
+ * training step is ~10 launches with no host synchronisation.  Replaces, per step, the op
+ * sequence of models/renderer.py:63-276 + models/fields.py:76-99 + exp_runner.py:191-207.
+ * All struct members are DEVICE pointers (or plain sizes).
+ * ===================================================================================== */
+#define SNB_NET_FLOATS 2432 /* folded MLP: W0T[35][64] | b0[64] | W1[64] | b1 | inv_s | pad */
+#define SNB_PATCH 9         /* rays per patch (3x3, config/diligent.conf:29) */
+
+typedef struct snb_net {
+    const void *table_f16;  /* [n_entries*2] fp16 hash table */
+    const float *net;       /* [SNB_NET_FLOATS] folded weights written by snb_prep_net */
+    snb_hashgrid_meta meta;
+    uint32_t n_active;      /* SDFNetwork.bindwidth (models/fields.py:73-83) */
+} snb_net;
+
+typedef struct snb_patch_batch { /* outputs of Dataset.gen_random_patches, models/dataset_loader.py:223-277 */
+    int32_t n_patches;
+    const float *rays_o;    /* [N,3]   camera centre of the patch's view */
+    const float *rays_d;    /* [N,9,3] */
+    const float *plane_n;   /* [N,3]   marching-plane normal */
+    const float *near_;     /* [N] */
+    const float *far_;      /* [N]   (NaN for rays missing the unit sphere) */
+    const float *v_inv;     /* [N,9,3,3] */
+    const float *normal_gt; /* [N,9,3] */
+    const float *mask;      /* [N,9] */
+} snb_patch_batch;
+
+typedef struct snb_samples { /* visible samples on the patch-centre rays, packed by patch */
+    int64_t capacity;       /* max samples S */
+    int64_t end_capacity;   /* max non-contiguous interval ends */
+    int32_t scratch_stride; /* per-ray capacity of the marching scratch */
+    int32_t *counts;        /* [N]   samples per ray */
+    int32_t *end_counts;    /* [N]   interval ends per ray that need their own SDF query */
+    int32_t *packed_info;   /* [N,2] (offset,count) */
+    int32_t *end_packed;    /* [N,2] */
+    int32_t *totals;        /* [4]   S, S_end, overflow flag, 0 */
+    float *t0;              /* [capacity] */
+    float *t1;              /* [capacity] */
+    int32_t *patch_idx;     /* [capacity] */
+    int32_t *end_slot;      /* [capacity] slot of the sample's own end query, or -1 (use next sample's start) */
+    int32_t *slot_sample;   /* [end_capacity] sample owning each end slot */
+    float *scratch_t0;      /* [N, scratch_stride] */
+    float *scratch_t1;      /* [N, scratch_stride] */
+} snb_samples;
+
+/* Fold weight_norm (models/fields.py:66-67) and the variance network (models/fields.py:133-139,
+ * models/renderer.py:171) into the `net` buffer; also reduces mask_sum (exp_runner.py:169-174).
+ * small layout: v0[64*d_in] | g0[64] | b0[64] | v1[64] | g1 | b1 | variance,  d_in = 3 + 2*n_levels.
+ * stats (device f32[8], zeroed here): [0]=mask_sum(+1e-5) [1]=normal sq-err sum [2]=bce sum
+ * [3]=eikonal sum [4]=d(inv_s) */
+int32_t snb_prep_net(int32_t n_levels, const float *small, float *net, int32_t n_mask, const float *mask,
+                     float *stats, snb_stream_t stream);
+/* Ray marching + NeuS visibility cut fused (NA/ray_marching.py:157-220 with
+ * models/renderer.py:80-122 as alpha_fn): warp per centre ray, stops at T < early_stop_eps.
+ * jitter: device f32[N] in [0,1) or null (stratified=False). */
+int32_t snb_march_visible(const snb_patch_batch *h_batch, const snb_net *h_net, const float *roi, int32_t res_x,
+                          int32_t res_y, int32_t res_z, const uint8_t *grid_binary, float step_size,
+                          const float *jitter, float early_stop_eps, const snb_samples *h_samples,
+                          snb_stream_t stream);
+/* scan counts -> packed_info/totals, then copy scratch -> packed arrays, assign end slots */
+int32_t snb_compact_samples(int32_t n_patches, const snb_samples *h_samples, snb_stream_t stream);
+/* SDF at arbitrary points, no grad.  mode 0: sdf, 1: sigmoid(-80*sdf) (models/renderer.py:56-60), 2: -sdf */
+int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *h_net, int32_t mode, float *out, snb_stream_t stream);
+/* SDF at the 9 plane-projected rays of every sample start (+ own ends), keeping the encoded features.
+ * sdf: [9*(capacity+end_capacity)]: starts at s*9+k, ends at 9*S + slot*9+k.  feats: half2 [points, n_levels] */
+int32_t snb_sdf_fwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                          float *sdf, void *feats, snb_stream_t stream);
+/* NeuS alpha -> patch transmittance scan -> dfd normals -> accumulation (models/renderer.py:164-267).
+ * comp [N,9,3], wsum [N,9]; optional per-sample outputs gradients [S,9,3], weights [S,9]. stats[3] += eikonal sum */
+int32_t snb_render_fwd(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                       const float *sdf, float *comp, float *wsum, float *gradients, float *weights, float *stats,
+                       snb_stream_t stream);
+/* losses of exp_runner.py:191-203 (l2) and their seeds: dcomp [N,9,3], dwsum [N,9]; stats[1], stats[2] */
+int32_t snb_patch_loss(const snb_patch_batch *h_batch, const float *comp, const float *wsum, float normal_weight,
+                       float mask_weight, float *stats, float *dcomp, float *dwsum, snb_stream_t stream);
+/* backward of snb_render_fwd: d_sdf0/d_sdf1 [S,9] (w.r.t. start / end SDF of each interval), stats[4] += d inv_s.
+ * dgrad [S,9,3] optional external seed on the per-sample gradients; eikonal_weight adds the fused
+ * eikonal term eikonal_weight * mean((|g|-1)^2). */
+int32_t snb_render_bwd(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                       const float *sdf, const float *comp, const float *wsum, const float *dcomp, const float *dwsum,
+                       const float *dgrad, float eikonal_weight, float *d_sdf0, float *d_sdf1, float *stats,
+                       snb_stream_t stream);
+/* MLP backward + hash-table scatter for all points of snb_sdf_fwd_patch.
+ * table_grad f32[n_entries*2] += ...;  net_grad f32[SNB_NET_FLOATS] += gradients w.r.t. the FOLDED weights */
+int32_t snb_sdf_bwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                          const void *feats, const float *d_sdf0, const float *d_sdf1, float *table_grad,
+                          float *net_grad, snb_stream_t stream);
+/* Un-fold net_grad into gradients of (v,g,b,variance) (weight_norm / exp backward), in `small` layout. */
+int32_t snb_unfold_grads(int32_t n_levels, const float *small, const float *net_grad, const float *stats,
+                         float *small_grad, snb_stream_t stream);
+/* Adam (torch.optim.Adam defaults, exp_runner.py:97,207) over n params; zeroes grad; optionally refreshes the
+ * fp16 copy.  step_count >= 1.  grad_scale multiplies the gradient first (1/world_size after an allreduce). */
+int32_t snb_adam_step(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *param_f16,
+                      float lr, float beta1, float beta2, float eps, int32_t step_count, float grad_scale,
+                      snb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,8 +84,25 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+LAUNCH_COUNT = 0
+# kernels launched per entry point (memsets not counted)
+KERNELS = {"snb_occgrid_binarize": 2, "snb_compact_samples": 2, "snb_max_i64": 2}
+
+
+PROFILE = None  # set to a list to record (name, start_event, end_event) around every call
+
+
 def call(name: str, *args) -> None:
-    check(getattr(lib(), name)(*args, stream()))
+    global LAUNCH_COUNT
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(*args, stream()))
+        e1.record()
+        PROFILE.append((name, e0, e1))
+    else:
+        check(getattr(lib(), name)(*args, stream()))
+    LAUNCH_COUNT += KERNELS.get(name, 1)
 
 
 def make_meta(n_levels, log2_hashmap_size, base_resolution, per_level_scale) -> Tuple[HashGridMeta, int]:

@@ -1,0 +1,259 @@
+// fused_march.cu -- occupancy-grid marching of the patch-centre rays fused with the NeuS visibility cut.
+//
+// Reference sequence (NA/ray_marching.py:157-220 driven by models/renderer.py:80-135): march every
+// centre ray to `far` (two kernel passes + cumsum + .item()), query the SDF at ALL S0 samples, CUB
+// exclusive product of (1-alpha), keep samples with T >= early_stop_eps, boolean-mask compaction
+// (nonzero -> another host sync).  Because T is non-increasing along a ray the kept samples are a
+// PREFIX of each ray's samples, so here one warp marches a ray in batches of 31 candidate samples
+// (same bit-exact stepping as march.cu), evaluates the SDF of that batch in-lane (encode + MLP, no
+// HBM round trip), multiplies T serially, and stops marching the moment T < eps: late in training
+// this evaluates ~S instead of ~S0 >> S points.  Samples go to a per-ray scratch; a device scan and
+// a copy kernel pack them by patch with no host round trip.
+#include "sdf_core.cuh"
+
+namespace snb {
+
+__device__ __forceinline__ float calc_dt_(float t, float cone, float dt_min) {
+    return fmaxf(dt_min, fminf(__fmul_rn(t, cone), 1e10f));
+}
+__device__ __forceinline__ bool occ_at(float x, float y, float z, const float *rmin, const float *rmax, int3 res,
+                                       const uint8_t *__restrict__ grid) {
+    if (x < rmin[0] || x > rmax[0] || y < rmin[1] || y > rmax[1] || z < rmin[2] || z > rmax[2]) return false;
+    float ux = __fdiv_rn(__fsub_rn(x, rmin[0]), __fsub_rn(rmax[0], rmin[0]));
+    float uy = __fdiv_rn(__fsub_rn(y, rmin[1]), __fsub_rn(rmax[1], rmin[1]));
+    float uz = __fdiv_rn(__fsub_rn(z, rmin[2]), __fsub_rn(rmax[2], rmin[2]));
+    int ix = min(max(__float2int_rz(__fmul_rn(ux, (float)res.x)), 0), res.x - 1);
+    int iy = min(max(__float2int_rz(__fmul_rn(uy, (float)res.y)), 0), res.y - 1);
+    int iz = min(max(__float2int_rz(__fmul_rn(uz, (float)res.z)), 0), res.z - 1);
+    return __ldg(grid + ((ix * res.y + iy) * res.z + iz)) != 0;
+}
+__device__ __forceinline__ float axis_dist_(float p, float dir, float inv_dir, float rmin, float rmax, int r) {
+    float rf = (float)r, ext = __fsub_rn(rmax, rmin);
+    float u = __fdiv_rn(__fsub_rn(p, rmin), ext);
+    float fl = floorf(__fmaf_rn(copysignf(1.0f, dir), 0.5f, __fmaf_rn(rf, u, 0.5f)));
+    return __fmul_rn(__fdiv_rn(__fmul_rn(__fmaf_rn(rf, -u, fl), inv_dir), rf), ext);
+}
+
+__global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, snb_net net, const float *__restrict__ roi,
+                                                            int3 res, const uint8_t *__restrict__ grid, float step,
+                                                            const float *__restrict__ jitter, float eps, snb_samples sm) {
+    __shared__ __align__(16) float s_net[kNetFloats];
+    load_net_to_smem(s_net, net.net);
+    const int lane = threadIdx.x & 31;
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= b.n_patches) return;
+    const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
+    const float inv_s = s_net[kOffInvS];
+
+    const float ox = __ldg(b.rays_o + 3 * ray), oy = __ldg(b.rays_o + 3 * ray + 1), oz = __ldg(b.rays_o + 3 * ray + 2);
+    const float *dc = b.rays_d + ((int64_t)ray * SNB_PATCH + SNB_PATCH / 2) * 3;  // centre ray of the patch
+    const float dx = __ldg(dc), dy = __ldg(dc + 1), dz = __ldg(dc + 2);
+    const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+    float near = __ldg(b.near_ + ray);
+    const float far = __ldg(b.far_ + ray);
+    if (jitter) near = __fadd_rn(near, __fmul_rn(__ldg(jitter + ray), step));  // NA/ray_marching.py:158
+    float rmin[3] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2)};
+    float rmax[3] = {__ldg(roi + 3), __ldg(roi + 4), __ldg(roi + 5)};
+
+    float *sc0 = sm.scratch_t0 + (int64_t)ray * sm.scratch_stride;
+    float *sc1 = sm.scratch_t1 + (int64_t)ray * sm.scratch_stride;
+
+    int j = 0, runs = 0;
+    bool chain_open = false, overflow = false;
+    float T = 1.f;
+    float t0 = near;
+    float t1 = __fadd_rn(t0, calc_dt_(t0, 0.f, step));
+    float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+
+    while (t_mid < far) {
+        float l0 = t0, l1 = t1;
+        for (int s = 0; s < lane; ++s) {
+            l0 = l1;
+            l1 = __fadd_rn(l0, calc_dt_(l0, 0.f, step));
+        }
+        float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
+        float px = __fmaf_rn(lm, dx, ox), py = __fmaf_rn(lm, dy, oy), pz = __fmaf_rn(lm, dz, oz);
+        bool in_range = lm < far;
+        bool occ = (lane < 31) && in_range && occ_at(px, py, pz, rmin, rmax, res, grid);
+        unsigned stop = ~__ballot_sync(0xffffffffu, occ);  // bit 31 always set: lane 31 only evaluates an end point
+        int f = __ffs(stop) - 1;                           // lanes [0,f) are samples, f <= 31
+        bool ray_done = false;
+        if (f > 0) {
+            // SDF at the start of every sample and (lane f) at the end of the last one; positions as the
+            // reference builds them: t_origins + t_dirs * t (models/renderer.py:84-86), separately rounded
+            float sdf = 0.f;
+            if (lane <= f)
+                sdf = sdf_point<false>(__fadd_rn(ox, __fmul_rn(dx, l0)), __fadd_rn(oy, __fmul_rn(dy, l0)),
+                                       __fadd_rn(oz, __fmul_rn(dz, l0)), table, net.meta, net.n_active, s_net, nullptr);
+            float sdf_next = __shfl_down_sync(0xffffffffu, sdf, 1);
+            float alpha = neus_alpha(sdf, sdf_next, inv_s);
+            int nvis = f;
+            for (int i = 0; i < f; ++i) {  // serial product, warp-uniform
+                float a = __shfl_sync(0xffffffffu, alpha, i);
+                if (!(T >= eps)) { nvis = i; break; }
+                T = __fmul_rn(T, __fsub_rn(1.f, a));
+            }
+            if (j + nvis > sm.scratch_stride) {
+                nvis = sm.scratch_stride - j;
+                overflow = true;
+            }
+            if (lane < nvis) {
+                sc0[j + lane] = l0;
+                sc1[j + lane] = l1;
+            }
+            if (nvis > 0 && !chain_open) ++runs;
+            j += nvis;
+            chain_open = (nvis == 31);
+            if (nvis < f || overflow) ray_done = true;
+        }
+        if (ray_done) break;
+        if (f == 31) {  // all 31 candidates were visible samples: continue contiguously
+            t0 = __shfl_sync(0xffffffffu, l1, 30);
+            t1 = __fadd_rn(t0, calc_dt_(t0, 0.f, step));
+            t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+            continue;
+        }
+        float s_mid = __shfl_sync(0xffffffffu, lm, f);
+        if (!(__shfl_sync(0xffffffffu, (int)in_range, f) != 0)) break;
+        float sx = __shfl_sync(0xffffffffu, px, f), sy = __shfl_sync(0xffffffffu, py, f), sz = __shfl_sync(0xffffffffu, pz, f);
+        float tx = axis_dist_(sx, dx, ix, rmin[0], rmax[0], res.x);
+        float ty = axis_dist_(sy, dy, iy, rmin[1], rmax[1], res.y);
+        float tz = axis_dist_(sz, dz, iz, rmin[2], rmax[2], res.z);
+        float t_target = fminf(__fadd_rn(s_mid, fmaxf(fminf(fminf(tx, ty), tz), 0.0f)), far);
+        float t = s_mid;
+        do {
+            t = __fadd_rn(t, step);
+        } while (t < t_target);
+        t_mid = t;
+        float dt = calc_dt_(t_mid, 0.f, step);
+        t0 = __fmaf_rn(dt, -0.5f, t_mid);
+        t1 = __fmaf_rn(dt, 0.5f, t_mid);
+    }
+    if (lane == 0) {
+        sm.counts[ray] = j;
+        sm.end_counts[ray] = runs;
+        if (overflow) atomicExch(sm.totals + 2, 1);
+    }
+}
+
+// One CTA: exclusive scans of the sample counts and the end counts, clipped to the capacities.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(int32_t n, snb_samples sm) {
+    __shared__ int32_t wsum[2][32];
+    __shared__ int32_t carry[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int32_t start = 0; start < n; start += 1024) {
+        int32_t i = start + threadIdx.x;
+        int32_t c[2] = {i < n ? sm.counts[i] : 0, i < n ? sm.end_counts[i] : 0};
+        int32_t v[2] = {c[0], c[1]};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t u = __shfl_up_sync(0xffffffffu, v[a], o);
+                if (lane >= o) v[a] += u;
+            }
+            if (lane == 31) wsum[a][warp] = v[a];
+        }
+        __syncthreads();
+        if (warp < 2) {
+            int32_t w = wsum[warp][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            wsum[warp][lane] = w;
+        }
+        __syncthreads();
+        int32_t incl[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) incl[a] = v[a] + (warp ? wsum[a][warp - 1] : 0) + carry[a];
+        if (i < n) {
+            int64_t cap[2] = {sm.capacity, sm.end_capacity};
+            int32_t *dst[2] = {sm.packed_info, sm.end_packed};
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                int64_t off = incl[a] - c[a];
+                int64_t cnt = c[a];
+                if (off >= cap[a]) { off = cap[a]; cnt = 0; }
+                else if (off + cnt > cap[a]) cnt = cap[a] - off;
+                dst[a][2 * i] = (int32_t)off;
+                dst[a][2 * i + 1] = (int32_t)cnt;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry[0] = incl[0]; carry[1] = incl[1]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (carry[0] > sm.capacity || carry[1] > sm.end_capacity) sm.totals[2] = 1;
+        sm.totals[0] = (int32_t)min((int64_t)carry[0], sm.capacity);
+        sm.totals[1] = (int32_t)min((int64_t)carry[1], sm.end_capacity);
+    }
+}
+
+// warp per ray: scratch -> packed (t0,t1,patch id), end-slot assignment.
+// An interval needs its own end query iff t1[i] != t0[i+1] (models/renderer.py:152-154); the last sample of a
+// ray always does (the reference compares it with the next ray's first start, which never matches).
+__global__ void __launch_bounds__(256) compact_kernel(int32_t n, snb_samples sm) {
+    const int lane = threadIdx.x & 31;
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n) return;
+    const int base = sm.packed_info[2 * ray], cnt = sm.packed_info[2 * ray + 1];
+    const int ebase = sm.end_packed[2 * ray], ecnt = sm.end_packed[2 * ray + 1];
+    const float *sc0 = sm.scratch_t0 + (int64_t)ray * sm.scratch_stride;
+    const float *sc1 = sm.scratch_t1 + (int64_t)ray * sm.scratch_stride;
+    int eused = 0;
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+        int j = j0 + lane;
+        bool valid = j < cnt;
+        float a0 = valid ? sc0[j] : 0.f, a1 = valid ? sc1[j] : 0.f;
+        float nxt = (valid && j + 1 < cnt) ? sc0[j + 1] : 0.f;
+        bool diff = valid && (j + 1 >= cnt || a1 != nxt);
+        unsigned dm = __ballot_sync(0xffffffffu, diff);
+        int slot = -1;
+        if (diff) {
+            int e = eused + __popc(dm & ((1u << lane) - 1u));
+            if (e < ecnt) slot = ebase + e;
+        }
+        eused += __popc(dm);
+        if (valid) {
+            sm.t0[base + j] = a0;
+            sm.t1[base + j] = a1;
+            sm.patch_idx[base + j] = ray;
+            sm.end_slot[base + j] = slot;
+            if (slot >= 0) sm.slot_sample[slot] = base + j;
+        }
+    }
+}
+
+}  // namespace snb
+using namespace snb;
+
+extern "C" int32_t snb_march_visible(const snb_patch_batch *b, const snb_net *net, const float *roi, int32_t rx, int32_t ry,
+                                     int32_t rz, const uint8_t *grid, float step, const float *jitter, float eps,
+                                     const snb_samples *sm, snb_stream_t stream) {
+    SNB_REQUIRE(b && net && sm, SNB_ERR_NULL, "march_visible: null struct");
+    SNB_REQUIRE(b->n_patches >= 0 && step > 0.f && rx > 0 && ry > 0 && rz > 0, SNB_ERR_ARG, "march_visible: bad sizes/step");
+    SNB_REQUIRE(net->n_active <= net->meta.n_levels && net->meta.n_levels <= SNB_MAX_LEVELS, SNB_ERR_ARG, "march_visible: bad level counts");
+    if (b->n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(b->rays_o && b->rays_d && b->near_ && b->far_ && roi && grid && net->table_f16 && net->net, SNB_ERR_NULL, "march_visible: null input");
+    SNB_REQUIRE(sm->counts && sm->end_counts && sm->totals && sm->scratch_t0 && sm->scratch_t1 && sm->scratch_stride > 0, SNB_ERR_NULL, "march_visible: null scratch");
+    SNB_REQUIRE(aligned(net->net, 16), SNB_ERR_ALIGN, "march_visible: net must be 16-byte aligned");
+    cudaMemsetAsync(sm->totals, 0, 4 * sizeof(int32_t), S(stream));
+    march_visible_kernel<<<(unsigned)cdiv(b->n_patches, 4), 128, 0, S(stream)>>>(*b, *net, roi, make_int3(rx, ry, rz), grid, step, jitter, eps, *sm);
+    SNB_LAUNCH_CHECK("march_visible");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_compact_samples(int32_t n, const snb_samples *sm, snb_stream_t stream) {
+    SNB_REQUIRE(sm, SNB_ERR_NULL, "compact_samples: null struct");
+    SNB_REQUIRE(n >= 0, SNB_ERR_ARG, "compact_samples: n < 0");
+    SNB_REQUIRE(sm->packed_info && sm->end_packed && sm->t0 && sm->t1 && sm->patch_idx && sm->end_slot && sm->slot_sample, SNB_ERR_NULL, "compact_samples: null buffer");
+    scan_counts_kernel<<<1, 1024, 0, S(stream)>>>(n, *sm);
+    if (n) compact_kernel<<<(unsigned)cdiv(n, 8), 256, 0, S(stream)>>>(n, *sm);
+    SNB_LAUNCH_CHECK("compact_samples");
+    return SNB_OK;
+}

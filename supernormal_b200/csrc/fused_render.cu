@@ -1,0 +1,321 @@
+// fused_render.cu -- NeuS alpha, patch-based transmittance scan, directional-finite-difference normals,
+// accumulation along rays and the training losses, forward and backward.
+//
+// Reference sequence: models/renderer.py:164-267 (≈40 ATen launches + the two nerfacc kernels
+// CS/render_weight.cu:87-118 / :298-340 + three scatter_add_) and exp_runner.py:191-203.
+// Here one warp owns one patch: lanes 0..26 = 3 consecutive samples x 9 in-patch rays.  The 3x3
+// neighbourhood a dfd normal needs is exchanged with warp shuffles, the transmittance product and the
+// backward suffix sum are carried along the samples in the reference's serial order
+// (w = a*T; T = T*(1-a)), and nothing per-sample is written except what the next kernel reads.
+#include "sdf_core.cuh"
+
+namespace snb {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct LaneGeom {     // per (patch, in-patch ray k) constants
+    float o[3], d[3], num, den;
+    int k, r, c, jj;
+    bool active;
+};
+
+__device__ __forceinline__ LaneGeom lane_geom(const snb_patch_batch &b, int patch, int lane) {
+    LaneGeom g;
+    g.active = lane < 27;
+    g.jj = g.active ? lane / 9 : 0;
+    g.k = g.active ? lane % 9 : 0;
+    g.r = g.k / 3;
+    g.c = g.k % 3;
+    const float *o = b.rays_o + 3 * (int64_t)patch;
+    const float *n = b.plane_n + 3 * (int64_t)patch;
+    const float *dk = b.rays_d + ((int64_t)patch * SNB_PATCH + g.k) * 3;
+    const float *dc = b.rays_d + ((int64_t)patch * SNB_PATCH + SNB_PATCH / 2) * 3;
+    float nx = __ldg(n), ny = __ldg(n + 1), nz = __ldg(n + 2);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        g.o[a] = __ldg(o + a);
+        g.d[a] = __ldg(dk + a);
+    }
+    g.num = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(dc), nx), __fmul_rn(__ldg(dc + 1), ny)), __fmul_rn(__ldg(dc + 2), nz));
+    g.den = __fadd_rn(__fadd_rn(__fmul_rn(g.d[0], nx), __fmul_rn(g.d[1], ny)), __fmul_rn(g.d[2], nz));
+    return g;
+}
+
+struct SampleVals {  // everything the forward and the backward recompute identically for one (sample, ray)
+    float s0, s1, dt, alpha, c, n, raw;
+    float dl, dr, du, dd;       // distances to the left / right / upper / lower neighbour on the marching plane
+    float proj[3];              // (df_dt, df_dx, df_dy)
+    float g[3];                 // V_inverse @ proj
+};
+
+__device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, float by, float bz) {
+    float x = ax - bx, y = ay - by, z = az - bz;
+    return sqrtf(x * x + y * y + z * z);
+}
+
+// All 32 lanes must call this (shuffles); `valid` lanes get meaningful values.
+__device__ __forceinline__ SampleVals sample_vals(const LaneGeom &lg, bool valid, int s, int S, const snb_samples &sm,
+                                                  const float *__restrict__ sdf, const float *vinv, float inv_s, int lane) {
+    SampleVals v;
+    float t0 = 0.f, t1 = 1.f;
+    v.s0 = v.s1 = 0.f;
+    if (valid) {
+        t0 = __ldg(sm.t0 + s);
+        t1 = __ldg(sm.t1 + s);
+        v.s0 = __ldg(sdf + (int64_t)s * SNB_PATCH + lg.k);
+        int slot = __ldg(sm.end_slot + s);
+        // models/renderer.py:164-169: end value = next interval's start unless the intervals are not contiguous
+        v.s1 = slot >= 0 ? __ldg(sdf + ((int64_t)S + slot) * SNB_PATCH + lg.k)
+                         : (s + 1 < S ? __ldg(sdf + (int64_t)(s + 1) * SNB_PATCH + lg.k) : v.s0);
+    }
+    float t0k = __fdiv_rn(__fmul_rn(t0, lg.num), lg.den), t1k = __fdiv_rn(__fmul_rn(t1, lg.num), lg.den);
+    float px = __fadd_rn(lg.o[0], __fmul_rn(lg.d[0], t0k));
+    float py = __fadd_rn(lg.o[1], __fmul_rn(lg.d[1], t0k));
+    float pz = __fadd_rn(lg.o[2], __fmul_rn(lg.d[2], t0k));
+    v.dt = t1k - t0k;
+    // 3x3 neighbourhood of the same sample lives in lanes jj*9 + k'
+    int ll = lg.c > 0 ? lane - 1 : lane, lr = lg.c < 2 ? lane + 1 : lane;
+    int lu = lg.r > 0 ? lane - 3 : lane, ld = lg.r < 2 ? lane + 3 : lane;
+    float sl = __shfl_sync(kFull, v.s0, ll), sr = __shfl_sync(kFull, v.s0, lr);
+    float su = __shfl_sync(kFull, v.s0, lu), sd = __shfl_sync(kFull, v.s0, ld);
+    v.dl = dist3(px, py, pz, __shfl_sync(kFull, px, ll), __shfl_sync(kFull, py, ll), __shfl_sync(kFull, pz, ll));
+    v.dr = dist3(__shfl_sync(kFull, px, lr), __shfl_sync(kFull, py, lr), __shfl_sync(kFull, pz, lr), px, py, pz);
+    v.du = dist3(px, py, pz, __shfl_sync(kFull, px, lu), __shfl_sync(kFull, py, lu), __shfl_sync(kFull, pz, lu));
+    v.dd = dist3(__shfl_sync(kFull, px, ld), __shfl_sync(kFull, py, ld), __shfl_sync(kFull, pz, ld), px, py, pz);
+    // models/renderer.py:194-212: forward difference along t, central / one-sided differences in the patch
+    v.proj[0] = (v.s1 - v.s0) / v.dt;
+    v.proj[1] = lg.c == 0 ? (sr - v.s0) / v.dr : (lg.c == 1 ? (sr - sl) / (v.dl + v.dr) : (v.s0 - sl) / v.dl);
+    v.proj[2] = lg.r == 0 ? (sd - v.s0) / v.dd : (lg.r == 1 ? (sd - su) / (v.dd + v.du) : (v.s0 - su) / v.du);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) v.g[a] = vinv[3 * a] * v.proj[0] + vinv[3 * a + 1] * v.proj[1] + vinv[3 * a + 2] * v.proj[2];
+    v.c = sigmoidf_(v.s0 * inv_s);
+    v.n = sigmoidf_(v.s1 * inv_s);
+    v.raw = (v.c - v.n + 1e-5f) / (v.c + 1e-5f);
+    v.alpha = fminf(fmaxf(v.raw, 0.f), 1.f);
+    if (!valid) {
+        v.alpha = 0.f;
+        v.g[0] = v.g[1] = v.g[2] = 0.f;
+    }
+    return v;
+}
+
+// serial chain over the three sample phases: returns this lane's value-before and updates the carry
+__device__ __forceinline__ float chain_mul(float &carry, float factor, const LaneGeom &lg) {
+    float f0 = __shfl_sync(kFull, factor, lg.k), f1 = __shfl_sync(kFull, factor, 9 + lg.k), f2 = __shfl_sync(kFull, factor, 18 + lg.k);
+    float T0 = carry, T1 = __fmul_rn(T0, f0), T2 = __fmul_rn(T1, f1);
+    carry = __fmul_rn(T2, f2);
+    return lg.jj == 0 ? T0 : (lg.jj == 1 ? T1 : T2);
+}
+__device__ __forceinline__ float chain_sub(float &carry, float term, const LaneGeom &lg) {
+    float f0 = __shfl_sync(kFull, term, lg.k), f1 = __shfl_sync(kFull, term, 9 + lg.k), f2 = __shfl_sync(kFull, term, 18 + lg.k);
+    float A0 = carry, A1 = A0 - f0, A2 = A1 - f1;
+    carry = A2 - f2;
+    return lg.jj == 0 ? A0 : (lg.jj == 1 ? A1 : A2);
+}
+
+__global__ void __launch_bounds__(128) render_fwd_kernel(snb_patch_batch b, const float *__restrict__ net, snb_samples sm,
+                                                         const float *__restrict__ sdf, float *__restrict__ comp,
+                                                         float *__restrict__ wsum, float *__restrict__ gradients,
+                                                         float *__restrict__ weights, float *__restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (patch >= b.n_patches) return;
+    const float inv_s = __ldg(net + kOffInvS);
+    const int S = sm.totals[0];
+    LaneGeom lg = lane_geom(b, patch, lane);
+    float vinv[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) vinv[a] = __ldg(b.v_inv + ((int64_t)patch * SNB_PATCH + lg.k) * 9 + a);
+    const int base = sm.packed_info[2 * patch], n = sm.packed_info[2 * patch + 1];
+    float Tc = 1.f, cn[3] = {0.f, 0.f, 0.f}, ws = 0.f, eik = 0.f;
+    for (int j0 = 0; j0 < n; j0 += 3) {
+        int j = j0 + lg.jj;
+        bool valid = lg.active && j < n;
+        int s = base + j;
+        SampleVals v = sample_vals(lg, valid, s, S, sm, sdf, vinv, inv_s, lane);
+        float T = chain_mul(Tc, __fsub_rn(1.f, v.alpha), lg);
+        float w = __fmul_rn(v.alpha, T);
+        if (valid) {
+            cn[0] += w * v.g[0]; cn[1] += w * v.g[1]; cn[2] += w * v.g[2];
+            ws += w;
+            float nrm = sqrtf(v.g[0] * v.g[0] + v.g[1] * v.g[1] + v.g[2] * v.g[2]);
+            eik += (nrm - 1.f) * (nrm - 1.f);
+            if (gradients) {
+                float *go = gradients + ((int64_t)s * SNB_PATCH + lg.k) * 3;
+                go[0] = v.g[0]; go[1] = v.g[1]; go[2] = v.g[2];
+            }
+            if (weights) weights[(int64_t)s * SNB_PATCH + lg.k] = w;
+        }
+    }
+    // fold the three sample phases: lanes 0..8 end with the per-ray totals
+#pragma unroll
+    for (int a = 0; a < 3; ++a) cn[a] += __shfl_down_sync(kFull, cn[a], 9) + __shfl_down_sync(kFull, cn[a], 18);
+    ws += __shfl_down_sync(kFull, ws, 9) + __shfl_down_sync(kFull, ws, 18);
+    if (lane < 9) {
+        float *co = comp + ((int64_t)patch * SNB_PATCH + lane) * 3;
+        co[0] = cn[0]; co[1] = cn[1]; co[2] = cn[2];
+        wsum[(int64_t)patch * SNB_PATCH + lane] = ws;
+    }
+    if (!lg.active) eik = 0.f;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) eik += __shfl_xor_sync(kFull, eik, o);
+    if (lane == 0 && stats && eik != 0.f) atomicAdd(stats + 3, eik);
+}
+
+// exp_runner.py:169-203: masked L2 normal loss / mask_sum, BCE on the rendered opacity; emits the seeds.
+__global__ void __launch_bounds__(256) patch_loss_kernel(int n_rays, const float *__restrict__ comp, const float *__restrict__ wsum,
+                                                         const float *__restrict__ gt, const float *__restrict__ mask,
+                                                         float normal_w, float mask_w, float *__restrict__ stats,
+                                                         float *__restrict__ dcomp, float *__restrict__ dwsum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float nsq = 0.f, bce = 0.f;
+    if (i < n_rays) {
+        float m = mask_w > 0.f ? (__ldg(mask + i) > 0.5f ? 1.f : 0.f) : 1.f;
+        float mask_sum = stats[0];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float e = (comp[3 * i + a] - __ldg(gt + 3 * i + a)) * m;
+            nsq += e * e;
+            dcomp[3 * i + a] = normal_w * 2.f * e * m / mask_sum;
+        }
+        float w = wsum[i];
+        float c = fminf(fmaxf(w, 1e-5f), 1.f - 1e-5f);
+        bce = -(m * logf(c) + (1.f - m) * logf(1.f - c));
+        bool pass = w >= 1e-5f && w <= 1.f - 1e-5f;
+        dwsum[i] = pass ? mask_w * (c - m) / (c * (1.f - c)) / (float)n_rays : 0.f;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        nsq += __shfl_xor_sync(kFull, nsq, o);
+        bce += __shfl_xor_sync(kFull, bce, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + 1, nsq);
+        atomicAdd(stats + 2, bce);
+    }
+}
+
+__global__ void __launch_bounds__(128) render_bwd_kernel(snb_patch_batch b, const float *__restrict__ net, snb_samples sm,
+                                                         const float *__restrict__ sdf, const float *__restrict__ comp,
+                                                         const float *__restrict__ wsum, const float *__restrict__ dcomp,
+                                                         const float *__restrict__ dwsum, const float *__restrict__ dgrad,
+                                                         float eik_w, float *__restrict__ d_sdf0, float *__restrict__ d_sdf1,
+                                                         float *__restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (patch >= b.n_patches) return;
+    const float inv_s = __ldg(net + kOffInvS);
+    const int S = sm.totals[0];
+    LaneGeom lg = lane_geom(b, patch, lane);
+    float vinv[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) vinv[a] = __ldg(b.v_inv + ((int64_t)patch * SNB_PATCH + lg.k) * 9 + a);
+    const int base = sm.packed_info[2 * patch], n = sm.packed_info[2 * patch + 1];
+    const int64_t rk = (int64_t)patch * SNB_PATCH + lg.k;
+    const float dc3[3] = {__ldg(dcomp + 3 * rk), __ldg(dcomp + 3 * rk + 1), __ldg(dcomp + 3 * rk + 2)};
+    const float dws = __ldg(dwsum + rk);
+    // sum_j gw_j w_j == <dcomp, comp> + dwsum * wsum   (gw_j = <dcomp, g_j> + dwsum)
+    float Ac = dc3[0] * __ldg(comp + 3 * rk) + dc3[1] * __ldg(comp + 3 * rk + 1) + dc3[2] * __ldg(comp + 3 * rk + 2) + dws * __ldg(wsum + rk);
+    float Tc = 1.f, dinv = 0.f;
+    const float eik_scale = S > 0 ? eik_w * 2.f / ((float)S * SNB_PATCH * 1.0f) : 0.f;
+    const int rowbase = lane - lg.c, colbase = lane - 3 * lg.r;
+    for (int j0 = 0; j0 < n; j0 += 3) {
+        int j = j0 + lg.jj;
+        bool valid = lg.active && j < n;
+        int s = base + j;
+        SampleVals v = sample_vals(lg, valid, s, S, sm, sdf, vinv, inv_s, lane);
+        float T = chain_mul(Tc, __fsub_rn(1.f, v.alpha), lg);
+        float w = __fmul_rn(v.alpha, T);
+        float gw = dc3[0] * v.g[0] + dc3[1] * v.g[1] + dc3[2] * v.g[2] + dws;
+        float A = chain_sub(Ac, valid ? gw * w : 0.f, lg);
+        // CS/render_weight.cu:323-338
+        float dalpha = (gw * T - A) / fmaxf(1.f - v.alpha, 1e-10f);
+        // d L / d g
+        float dg[3];
+        float nrm = sqrtf(v.g[0] * v.g[0] + v.g[1] * v.g[1] + v.g[2] * v.g[2]);
+        float ek = nrm > 0.f ? eik_scale * (nrm - 1.f) / nrm : 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dg[a] = w * dc3[a] + ek * v.g[a];
+        if (dgrad && valid) {
+            const float *ge = dgrad + ((int64_t)s * SNB_PATCH + lg.k) * 3;
+            dg[0] += __ldg(ge); dg[1] += __ldg(ge + 1); dg[2] += __ldg(ge + 2);
+        }
+        float q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) q[a] = vinv[a] * dg[0] + vinv[3 + a] * dg[1] + vinv[6 + a] * dg[2];  // V^T dg
+        // alpha backward (clip passes the gradient on the closed interval, like torch.clamp)
+        float ds0 = 0.f, ds1 = 0.f;
+        if (v.raw >= 0.f && v.raw <= 1.f) {
+            float ce = v.c + 1e-5f;
+            float dcdf = dalpha * v.n / (ce * ce), dndf = -dalpha / ce;
+            float gc = v.c * (1.f - v.c), gn = v.n * (1.f - v.n);
+            ds0 = dcdf * gc * inv_s;
+            ds1 = dndf * gn * inv_s;
+            if (valid) dinv += dcdf * gc * v.s0 + dndf * gn * v.s1;
+        }
+        // dfd backward
+        float ut = q[0] / v.dt;
+        ds1 += ut;
+        ds0 -= ut;
+        float ux = q[1] / (lg.c == 0 ? v.dr : (lg.c == 1 ? v.dl + v.dr : v.dl));
+        float uy = q[2] / (lg.r == 0 ? v.dd : (lg.r == 1 ? v.dd + v.du : v.du));
+        if (!valid) ux = uy = 0.f;
+        float ux0 = __shfl_sync(kFull, ux, rowbase), ux1 = __shfl_sync(kFull, ux, rowbase + 1), ux2 = __shfl_sync(kFull, ux, rowbase + 2);
+        float uy0 = __shfl_sync(kFull, uy, colbase), uy1 = __shfl_sync(kFull, uy, colbase + 3), uy2 = __shfl_sync(kFull, uy, colbase + 6);
+        ds0 += lg.c == 0 ? (-ux0 - ux1) : (lg.c == 1 ? (ux0 - ux2) : (ux1 + ux2));
+        ds0 += lg.r == 0 ? (-uy0 - uy1) : (lg.r == 1 ? (uy0 - uy2) : (uy1 + uy2));
+        if (valid) {
+            d_sdf0[(int64_t)s * SNB_PATCH + lg.k] = ds0;
+            d_sdf1[(int64_t)s * SNB_PATCH + lg.k] = ds1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dinv += __shfl_xor_sync(kFull, dinv, o);
+    if (lane == 0 && dinv != 0.f) atomicAdd(stats + 4, dinv);
+}
+
+}  // namespace snb
+using namespace snb;
+
+static int32_t check_render(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const char *who) {
+    SNB_REQUIRE(b && net && sm, SNB_ERR_NULL, "%s: null struct", who);
+    SNB_REQUIRE(b->n_patches >= 0, SNB_ERR_ARG, "%s: n_patches < 0", who);
+    SNB_REQUIRE(b->rays_o && b->rays_d && b->plane_n && b->v_inv && net->net, SNB_ERR_NULL, "%s: null batch buffer", who);
+    SNB_REQUIRE(sm->totals && sm->t0 && sm->t1 && sm->end_slot && sm->packed_info, SNB_ERR_NULL, "%s: null samples", who);
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_render_fwd(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const float *sdf, float *comp,
+                                  float *wsum, float *gradients, float *weights, float *stats, snb_stream_t stream) {
+    int32_t rc = check_render(b, net, sm, "render_fwd");
+    if (rc) return rc;
+    if (b->n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(sdf && comp && wsum, SNB_ERR_NULL, "render_fwd: null buffer");
+    render_fwd_kernel<<<(unsigned)cdiv(b->n_patches, 4), 128, 0, S(stream)>>>(*b, net->net, *sm, sdf, comp, wsum, gradients, weights, stats);
+    SNB_LAUNCH_CHECK("render_fwd");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_patch_loss(const snb_patch_batch *b, const float *comp, const float *wsum, float normal_weight,
+                                  float mask_weight, float *stats, float *dcomp, float *dwsum, snb_stream_t stream) {
+    SNB_REQUIRE(b, SNB_ERR_NULL, "patch_loss: null batch");
+    if (b->n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(comp && wsum && b->normal_gt && b->mask && stats && dcomp && dwsum, SNB_ERR_NULL, "patch_loss: null buffer");
+    int n = b->n_patches * SNB_PATCH;
+    patch_loss_kernel<<<(unsigned)cdiv(n, 256), 256, 0, S(stream)>>>(n, comp, wsum, b->normal_gt, b->mask, normal_weight, mask_weight, stats, dcomp, dwsum);
+    SNB_LAUNCH_CHECK("patch_loss");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_render_bwd(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const float *sdf,
+                                  const float *comp, const float *wsum, const float *dcomp, const float *dwsum, const float *dgrad,
+                                  float eikonal_weight, float *d_sdf0, float *d_sdf1, float *stats, snb_stream_t stream) {
+    int32_t rc = check_render(b, net, sm, "render_bwd");
+    if (rc) return rc;
+    if (b->n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(sdf && comp && wsum && dcomp && dwsum && d_sdf0 && d_sdf1 && stats, SNB_ERR_NULL, "render_bwd: null buffer");
+    render_bwd_kernel<<<(unsigned)cdiv(b->n_patches, 4), 128, 0, S(stream)>>>(*b, net->net, *sm, sdf, comp, wsum, dcomp, dwsum, dgrad,
+                                                                            eikonal_weight, d_sdf0, d_sdf1, stats);
+    SNB_LAUNCH_CHECK("render_bwd");
+    return SNB_OK;
+}

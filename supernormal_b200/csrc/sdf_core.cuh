@@ -1,0 +1,116 @@
+// sdf_core.cuh -- per-thread fused "hash-grid encode -> 64-wide SDF MLP" used by every fused kernel.
+//
+// Restates models/fields.py:76-99 (SDFNetwork.forward): x_in = [x, enc(x)*level_mask];
+// h = softplus_100(W0 x_in + b0); sdf = W1 h + b1, with W = g*v/||v|| (weight_norm) folded on the
+// device once per step by prep_net (optim.cu).  The encoding half is fp16-faithful tiny-cuda-nn
+// (hashgrid.cuh); the MLP is fp32 like the reference's torch.nn.Linear.
+//
+// Layout of the folded network ("net" buffer, floats), input-major so that one input feature's 64
+// weights are a contiguous, warp-broadcast float4 stream from shared memory:
+//   W0T[DIN_MAX][64] | b0[64] | W1[64] | b1 | inv_s | pad
+#pragma once
+#include "hashgrid.cuh"
+
+namespace snb {
+
+constexpr int kH = SNB_HIDDEN;          // 64
+constexpr int kDinMax = 3 + 2 * SNB_MAX_LEVELS;  // 35
+constexpr int kOffW0T = 0;
+constexpr int kOffB0 = kDinMax * kH;    // 2240
+constexpr int kOffW1 = kOffB0 + kH;     // 2304
+constexpr int kOffB1 = kOffW1 + kH;     // 2368
+constexpr int kOffInvS = kOffB1 + 1;    // 2369
+constexpr int kNetFloats = 2432;        // padded to a multiple of 64
+
+__device__ __forceinline__ void load_net_to_smem(float *s_net, const float *__restrict__ g_net) {
+    const float4 *src = reinterpret_cast<const float4 *>(g_net);
+    float4 *dst = reinterpret_cast<float4 *>(s_net);
+    for (int i = threadIdx.x; i < kNetFloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// softplus(beta=100, threshold=20) and its derivative sigmoid(100 z)   (models/fields.py:70)
+__device__ __forceinline__ float softplus100(float z) {
+    float bz = 100.f * z;
+    return bz > 20.f ? z : log1pf(expf(bz)) * 0.01f;
+}
+__device__ __forceinline__ float softplus100_grad(float z) {
+    float bz = 100.f * z;
+    return bz > 20.f ? 1.f : 1.f / (1.f + expf(-bz));
+}
+
+__device__ __forceinline__ void rank1_update(float (&acc)[kH], const float *__restrict__ w_row, float v) {
+    const float4 *w = reinterpret_cast<const float4 *>(w_row);
+#pragma unroll
+    for (int q = 0; q < kH / 4; ++q) {
+        float4 t = w[q];
+        acc[4 * q + 0] = fmaf(t.x, v, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(t.y, v, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(t.z, v, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(t.w, v, acc[4 * q + 3]);
+    }
+}
+
+// Pre-activations z[64] of layer 0 for one point.  feat_row (optional, global, half2[L]) receives the
+// encoded features of the active levels so the backward can skip the gathers.
+template <bool SAVE_FEAT, bool LOAD_FEAT>
+__device__ __forceinline__ void layer0(float x, float y, float z, const __half2 *__restrict__ table,
+                                       const snb_hashgrid_meta &m, uint32_t n_active, const float *s_net,
+                                       __half2 *feat_row, float (&acc)[kH]) {
+    const float4 *b0 = reinterpret_cast<const float4 *>(s_net + kOffB0);
+#pragma unroll
+    for (int q = 0; q < kH / 4; ++q) {
+        float4 t = b0[q];
+        acc[4 * q] = t.x; acc[4 * q + 1] = t.y; acc[4 * q + 2] = t.z; acc[4 * q + 3] = t.w;
+    }
+    rank1_update(acc, s_net + kOffW0T + 0 * kH, x);
+    rank1_update(acc, s_net + kOffW0T + 1 * kH, y);
+    rank1_update(acc, s_net + kOffW0T + 2 * kH, z);
+    for (uint32_t l = 0; l < n_active; ++l) {
+        __half2 f;
+        if (LOAD_FEAT) {
+            f = feat_row[l];
+        } else {
+            LevelCtx c = level_ctx(m, l);
+            Cell cell = cell_of(c, x, y, z);
+            f = interp_level(c, cell, table);
+            if (SAVE_FEAT) feat_row[l] = f;
+        }
+        float2 ff = __half22float2(f);
+        rank1_update(acc, s_net + kOffW0T + (3 + 2 * l) * kH, ff.x);
+        rank1_update(acc, s_net + kOffW0T + (4 + 2 * l) * kH, ff.y);
+    }
+}
+
+__device__ __forceinline__ float layer1(const float (&acc)[kH], const float *s_net) {
+    float s = s_net[kOffB1];
+    const float4 *w1 = reinterpret_cast<const float4 *>(s_net + kOffW1);
+#pragma unroll
+    for (int q = 0; q < kH / 4; ++q) {
+        float4 t = w1[q];
+        s = fmaf(t.x, softplus100(acc[4 * q + 0]), s);
+        s = fmaf(t.y, softplus100(acc[4 * q + 1]), s);
+        s = fmaf(t.z, softplus100(acc[4 * q + 2]), s);
+        s = fmaf(t.w, softplus100(acc[4 * q + 3]), s);
+    }
+    return s;
+}
+
+template <bool SAVE_FEAT>
+__device__ __forceinline__ float sdf_point(float x, float y, float z, const __half2 *__restrict__ table,
+                                           const snb_hashgrid_meta &m, uint32_t n_active, const float *s_net,
+                                           __half2 *feat_row) {
+    float acc[kH];
+    layer0<SAVE_FEAT, false>(x, y, z, table, m, n_active, s_net, feat_row, acc);
+    return layer1(acc, s_net);
+}
+
+// NeuS opacity of an interval from the SDF at its two ends (models/renderer.py:173-179)
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float neus_alpha(float s0, float s1, float inv_s) {
+    float c = sigmoidf_(s0 * inv_s), n = sigmoidf_(s1 * inv_s);
+    float a = (c - n + 1e-5f) / (c + 1e-5f);
+    return fminf(fmaxf(a, 0.f), 1.f);
+}
+
+}  // namespace snb

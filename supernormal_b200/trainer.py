@@ -1,0 +1,366 @@
+"""Fused, sync-free training step for SuperNormal's patch-based NeuS (the hot loop of
+exp_runner.py:147-210 = Runner.train, around models/renderer.py:63-276 and models/fields.py:76-99).
+
+Host side only: schedules, buffer ownership and ~10 C-ABI calls per iteration.  All tensor math runs
+in libsnb200 (hand-written sm_100a kernels); there is no PyTorch/CPU fallback.  State-dict keys of the
+reference (`encoding.params`, `lin{0,1}.{weight_g,weight_v,bias}`, `variance`) are
+produced / consumed by `reference_state_dict` / `load_reference_state_dict`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HashGridMeta, call, ptr
+
+H = 64
+NET_FLOATS = 2432
+P = 9
+SMALL_PAD = 2560  # floats reserved for the MLP/variance parameters in front of the hash table (16B aligned)
+
+
+class SnbNet(C.Structure):
+    _fields_ = [("table_f16", C.c_void_p), ("net", C.c_void_p), ("meta", HashGridMeta), ("n_active", C.c_uint32)]
+
+
+class SnbPatchBatch(C.Structure):
+    _fields_ = [("n_patches", C.c_int32), ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("plane_n", C.c_void_p),
+                ("near_", C.c_void_p), ("far_", C.c_void_p), ("v_inv", C.c_void_p), ("normal_gt", C.c_void_p),
+                ("mask", C.c_void_p)]
+
+
+class SnbSamples(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("end_capacity", C.c_int64), ("scratch_stride", C.c_int32),
+                ("counts", C.c_void_p), ("end_counts", C.c_void_p), ("packed_info", C.c_void_p),
+                ("end_packed", C.c_void_p), ("totals", C.c_void_p), ("t0", C.c_void_p), ("t1", C.c_void_p),
+                ("patch_idx", C.c_void_p), ("end_slot", C.c_void_p), ("slot_sample", C.c_void_p),
+                ("scratch_t0", C.c_void_p), ("scratch_t1", C.c_void_p)]
+
+
+class SDFModel:
+    """Parameters of SDFNetwork (models/fields.py:7-99, shipped configuration: one 64-wide hidden layer,
+    weight-norm, Softplus(beta=100), input_concat, geometric init) + SingleVarianceNetwork
+    (models/fields.py:133-139) in ONE flat fp32 buffer:  [ small | pad | hash table ]
+        small = v0[64, d_in] | g0[64] | b0[64] | v1[64] | g1 | b1 | variance,   d_in = 3 + 2*n_levels
+    so that Adam and the data-parallel allreduce are single contiguous sweeps.  A persistent fp16 copy
+    of the table (what tiny-cuda-nn gathers from) is refreshed by the optimizer kernel."""
+
+    def __init__(self, encoding_config: dict, bias: float = 0.6, variance_init: float = 0.5, seed: int = 1337, device="cuda"):
+        cfg = dict(encoding_config)
+        self.n_levels = int(cfg["n_levels"])
+        assert int(cfg.get("n_features_per_level", 2)) == 2
+        self.meta, self.n_entries = _lib.make_meta(self.n_levels, int(cfg["log2_hashmap_size"]), int(cfg["base_resolution"]),
+                                                   float(cfg["per_level_scale"]))
+        self.offsets = [int(self.meta.offsets[i]) for i in range(self.n_levels + 1)]
+        self.d_in = 3 + 2 * self.n_levels
+        self.n_small = H * self.d_in + 3 * H + 3
+        assert self.n_small <= SMALL_PAD
+        self.n_table = self.n_entries * 2
+        self.device = torch.device(device)
+        g = torch.Generator().manual_seed(seed)
+        flat = torch.zeros(SMALL_PAD + self.n_table)
+        flat[SMALL_PAD:] = (torch.rand(self.n_table, generator=g) * 2 - 1) * 1e-4   # tcnn init U(-1e-4, 1e-4)
+        # geometric init, models/fields.py:47-65 (l == 0 with encoding; l == num_layers-2), then weight_norm: g = |v|
+        w0 = torch.zeros(H, self.d_in)
+        w0[:, :3].normal_(0.0, math.sqrt(2) / math.sqrt(H), generator=g)
+        w1 = torch.empty(H).normal_(math.sqrt(math.pi) / math.sqrt(H), 1e-4, generator=g)
+        o = self._small_offsets()
+        flat[o["v0"]:o["g0"]] = w0.flatten()
+        flat[o["g0"]:o["b0"]] = w0.norm(dim=1)
+        flat[o["v1"]:o["g1"]] = w1
+        flat[o["g1"]] = w1.norm()
+        flat[o["b1"]] = -bias
+        flat[o["var"]] = variance_init
+        self.flat = flat.to(self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.table_f16 = torch.empty(self.n_table, dtype=torch.float16, device=self.device)
+        self.net = torch.zeros(NET_FLOATS, device=self.device)
+        self.net_grad = torch.zeros(NET_FLOATS, device=self.device)
+        self.n_active = 0  # SDFNetwork.bindwidth
+        self.refresh_table_f16()
+
+    def _small_offsets(self) -> Dict[str, int]:
+        v0 = 0
+        g0 = H * self.d_in
+        b0 = g0 + H
+        v1 = b0 + H
+        g1 = v1 + H
+        return dict(v0=v0, g0=g0, b0=b0, v1=v1, g1=g1, b1=g1 + 1, var=g1 + 2)
+
+    @property
+    def small(self):
+        return self.flat[:self.n_small]
+
+    @property
+    def table(self):
+        return self.flat[SMALL_PAD:]
+
+    def refresh_table_f16(self):
+        call("snb_cast_f32_to_f16", self.n_table, ptr(self.table), ptr(self.table_f16))
+
+    def net_struct(self) -> SnbNet:
+        return SnbNet(self.table_f16.data_ptr(), self.net.data_ptr(), self.meta, self.n_active)
+
+    def prep(self, mask: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None):
+        """weight_norm + variance folding (-> self.net); optionally mask_sum and stats reset."""
+        call("snb_prep_net", self.n_levels, ptr(self.small), ptr(self.net), 0 if mask is None else mask.numel(),
+             ptr(mask), ptr(stats))
+
+    @torch.no_grad()
+    def sdf(self, x: torch.Tensor, mode: int = 0) -> torch.Tensor:
+        """SDFNetwork.sdf under no_grad (mode 1: occ_eval_fn of models/renderer.py:56-60, mode 2: -sdf)."""
+        x = x.contiguous().float()
+        out = torch.empty(x.shape[0], device=x.device)
+        net = self.net_struct()
+        call("snb_sdf_eval", x.shape[0], ptr(x), C.byref(net), mode, ptr(out))
+        return out.unsqueeze(-1)
+
+    # -- reference checkpoint format (exp_runner.py:298-315) --------------------------------------
+    def reference_state_dict(self) -> Dict[str, torch.Tensor]:
+        o, s = self._small_offsets(), self.small
+        return {
+            "sdf_network_fine": {
+                "encoding.params": self.table.clone(),
+                "lin0.bias": s[o["b0"]:o["v1"]].clone(), "lin0.weight_g": s[o["g0"]:o["b0"]].clone().view(H, 1),
+                "lin0.weight_v": s[o["v0"]:o["g0"]].clone().view(H, self.d_in),
+                "lin1.bias": s[o["b1"]:o["b1"] + 1].clone(), "lin1.weight_g": s[o["g1"]:o["g1"] + 1].clone().view(1, 1),
+                "lin1.weight_v": s[o["v1"]:o["g1"]].clone().view(1, H)},
+            "variance_network_fine": {"variance": s[o["var"]].clone()},
+        }
+
+    @torch.no_grad()
+    def load_reference_state_dict(self, sd: Dict[str, Dict[str, torch.Tensor]]):
+        o, s = self._small_offsets(), self.small
+        f = {k: v.to(self.device).float() for k, v in sd["sdf_network_fine"].items()}
+        self.table.copy_(f["encoding.params"].flatten())
+        s[o["v0"]:o["g0"]] = f["lin0.weight_v"].flatten()
+        s[o["g0"]:o["b0"]] = f["lin0.weight_g"].flatten()
+        s[o["b0"]:o["v1"]] = f["lin0.bias"].flatten()
+        s[o["v1"]:o["g1"]] = f["lin1.weight_v"].flatten()
+        s[o["g1"]] = f["lin1.weight_g"].flatten()[0]
+        s[o["b1"]] = f["lin1.bias"].flatten()[0]
+        s[o["var"]] = sd["variance_network_fine"]["variance"].to(self.device).float()
+        self.refresh_table_f16()
+
+
+class SampleBuffers:
+    """Capacity buffers for the data-dependent sample lists (no host sync, SURVEY §7 'Dynamic sizes')."""
+
+    def __init__(self, n_patches: int, samples_per_ray_cap: int, scratch_stride: int, n_levels: int, device):
+        self.n_patches = n_patches
+        self.capacity = n_patches * samples_per_ray_cap
+        self.end_capacity = max(n_patches * 8, self.capacity // 4)
+        i32 = dict(dtype=torch.int32, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.counts = torch.zeros(n_patches, **i32)
+        self.end_counts = torch.zeros(n_patches, **i32)
+        self.packed_info = torch.zeros(n_patches, 2, **i32)
+        self.end_packed = torch.zeros(n_patches, 2, **i32)
+        self.totals = torch.zeros(4, **i32)
+        self.t0 = torch.zeros(self.capacity, **f32)
+        self.t1 = torch.zeros(self.capacity, **f32)
+        self.patch_idx = torch.zeros(self.capacity, **i32)
+        self.end_slot = torch.zeros(self.capacity, **i32)
+        self.slot_sample = torch.zeros(self.end_capacity, **i32)
+        self.scratch_stride = scratch_stride
+        self.scratch_t0 = torch.zeros(n_patches * scratch_stride, **f32)
+        self.scratch_t1 = torch.zeros(n_patches * scratch_stride, **f32)
+        m_cap = P * (self.capacity + self.end_capacity)
+        self.sdf = torch.zeros(m_cap, **f32)
+        self.feats = torch.zeros(m_cap * n_levels * 2, dtype=torch.float16, device=device)
+        self.d_sdf0 = torch.zeros(P * self.capacity, **f32)
+        self.d_sdf1 = torch.zeros(P * self.capacity, **f32)
+        self.comp = torch.zeros(n_patches, P, 3, **f32)
+        self.wsum = torch.zeros(n_patches, P, **f32)
+        self.dcomp = torch.zeros(n_patches, P, 3, **f32)
+        self.dwsum = torch.zeros(n_patches, P, **f32)
+        self.stats = torch.zeros(8, **f32)
+        self.struct = SnbSamples(self.capacity, self.end_capacity, scratch_stride, *[t.data_ptr() for t in (
+            self.counts, self.end_counts, self.packed_info, self.end_packed, self.totals, self.t0, self.t1,
+            self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1)])
+
+
+def make_batch_struct(rays_o, rays_d, plane_n, near, far, v_inv, normal_gt, mask) -> SnbPatchBatch:
+    """rays_o may be [N,3] or the reference's expanded [N,3,3,3] (only the centre origin is read)."""
+    n = rays_d.shape[0]
+    return SnbPatchBatch(n, *[0 if t is None else t.data_ptr() for t in (rays_o, rays_d, plane_n, near, far, v_inv, normal_gt, mask)])
+
+
+class FusedTrainer:
+    """Runner.train (exp_runner.py:147-210) on the fused kernels.  One process per GPU; with
+    torch.distributed initialised, gradients are all-reduced (sum) over NCCL before Adam and divided by
+    the world size (each rank draws its own patches: weak scaling)."""
+
+    def __init__(self, dataset, conf: dict, device="cuda", seed: int = 0, samples_per_ray_cap: int = 320,
+                 world_size: int = 1, rank: int = 0):
+        self.ds, self.conf, self.device = dataset, conf, torch.device(device)
+        self.world_size, self.rank = world_size, rank
+        self.n_patches = int(conf["batch_size"])
+        assert int(conf["patch_size"]) == 3, "3x3 patches (config/diligent.conf:29)"
+        assert conf.get("gradient_method", "dfd") == "dfd", "fused path implements dfd (the shipped default)"
+        self.model = SDFModel(conf["encoding"], conf["sdf_network"]["bias"], conf["variance_init"], device=self.device)
+        rm = conf["ray_marching"]
+        self.start_step, self.end_step = float(rm["start_step_size"]), float(rm["end_step_size"])
+        self.slop = (math.log10(self.start_step) - math.log10(self.end_step)) / conf["end_iter"]
+        stride = int(2.0 / self.end_step) + 64
+        self.buf = SampleBuffers(self.n_patches, samples_per_ray_cap, stride, self.model.n_levels, self.device)
+        from .nerfacc_api import OccupancyGrid
+        self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
+        self.iter_step = 0
+        self.lr = float(conf["learning_rate"])  # Adam's constructor value is what step 0 uses (exp_runner.py:97,210)
+        self.gen = torch.Generator(device=self.device).manual_seed(seed + rank)
+        self.np_rng = np.random.RandomState(seed + rank)
+        self.last_batch = None
+
+    # -- schedule pieces -----------------------------------------------------------------------
+    def step_size(self, it: int) -> float:
+        return float(np.float32(10 ** (math.log10(self.start_step) - self.slop * it)))
+
+    def _lr_factor(self) -> float:
+        c = self.conf
+        if self.iter_step < c["warm_up_end"]:
+            return self.iter_step / c["warm_up_end"]
+        prog = (self.iter_step - c["warm_up_end"]) / (c["end_iter"] - c["warm_up_end"])
+        return (math.cos(math.pi * prog) + 1.0) * 0.5 * (1 - c["learning_rate_alpha"]) + c["learning_rate_alpha"]
+
+    def update_occupancy(self, it: int):
+        rm = self.conf["ray_marching"]
+        self.model.prep()
+        self.grid._update(step=it, occ_eval_fn=lambda x: self.model.sdf(x, mode=1), occ_thre=rm["occ_threshold"])
+
+    def sample_batch(self):
+        c = self.conf
+        o, d, pn, vinv, nrm, msk = self.ds.gen_random_patches(self.n_patches, c["patch_size"], c["patch_size"],
+                                                              generator=self.gen, np_rng=self.np_rng)
+        near, far = self.ds.near_far_from_sphere(o[:, 1, 1], d[:, 1, 1])
+        return dict(rays_o=o[:, 1, 1].contiguous(), rays_d=d.view(-1, P, 3), plane_n=pn, near=near.contiguous(),
+                    far=far.contiguous(), v_inv=vinv.view(-1, P, 9), normal_gt=nrm.view(-1, P, 3), mask=msk.view(-1, P).contiguous())
+
+    # -- one iteration ---------------------------------------------------------------------------
+    def forward_backward(self, batch: dict, step_size: float, jitter: Optional[torch.Tensor]):
+        """march -> sdf -> render -> loss -> backward; leaves gradients in model.grad (small + table)."""
+        m, b = self.model, self.buf
+        c = self.conf
+        bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"],
+                               batch["v_inv"], batch["normal_gt"], batch["mask"])
+        self.last_batch = batch
+        m.prep(batch["mask"], b.stats)
+        net = m.net_struct()
+        rb, rn, rs = C.byref(bs), C.byref(net), C.byref(b.struct)
+        res = self.grid._res
+        grid_u8 = self.grid.binary.view(torch.uint8)
+        call("snb_march_visible", rb, rn, ptr(self.grid.roi_aabb), *res, ptr(grid_u8), float(step_size), ptr(jitter), 1e-8, rs)
+        call("snb_compact_samples", self.n_patches, rs)
+        call("snb_sdf_fwd_patch", rb, rn, rs, ptr(b.sdf), ptr(b.feats))
+        call("snb_render_fwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), None, None, ptr(b.stats))
+        call("snb_patch_loss", rb, ptr(b.comp), ptr(b.wsum), float(c["normal_weight"]), float(c["mask_weight"]), ptr(b.stats),
+             ptr(b.dcomp), ptr(b.dwsum))
+        call("snb_render_bwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), ptr(b.dcomp), ptr(b.dwsum), None,
+             float(c["eikonal_weight"]), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
+        m.net_grad.zero_()
+        call("snb_sdf_bwd_patch", rb, rn, rs, ptr(b.feats), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
+        call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(b.stats), ptr(m.grad))
+
+    def optimizer_step(self):
+        m = self.model
+        n_live = SMALL_PAD + 2 * m.offsets[m.n_active]  # zero-gradient levels are exact no-ops for Adam without weight decay
+        gscale = 1.0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(m.grad[:n_live])
+            gscale = 1.0 / self.world_size
+        t = self.iter_step + 1
+        call("snb_adam_step", SMALL_PAD, ptr(m.flat), ptr(m.grad), ptr(m.exp_avg), ptr(m.exp_avg_sq), None,
+             self.lr, 0.9, 0.999, 1e-8, t, gscale)
+        nt = n_live - SMALL_PAD
+        if nt > 0:
+            call("snb_adam_step", nt, ptr(m.flat[SMALL_PAD:]), ptr(m.grad[SMALL_PAD:]), ptr(m.exp_avg[SMALL_PAD:]),
+                 ptr(m.exp_avg_sq[SMALL_PAD:]), ptr(m.table_f16), self.lr, 0.9, 0.999, 1e-8, t, gscale)
+
+    def train_step(self, batch: Optional[dict] = None, jitter: Optional[torch.Tensor] = None):
+        c, rm = self.conf, self.conf["ray_marching"]
+        it = self.iter_step
+        if it % rm["occ_update_freq"] == 0:
+            self.update_occupancy(it)
+        if it % c["increase_bindwidth_every"] == 0:
+            self.model.n_active = min(self.model.n_active + 1, self.model.n_levels)
+        if batch is None:
+            batch = self.sample_batch()
+        if jitter is None:
+            jitter = torch.rand(self.n_patches, device=self.device, generator=self.gen)
+        self.forward_backward(batch, self.step_size(it), jitter)
+        self.optimizer_step()
+        self.iter_step += 1
+        self.lr = self.conf["learning_rate"] * self._lr_factor()
+
+    # -- host-side readbacks (sync) ---------------------------------------------------------------
+    def loss_terms(self) -> Dict[str, float]:
+        st = self.buf.stats.cpu().tolist()
+        tot = self.buf.totals.cpu().tolist()
+        S = max(tot[0], 1)
+        c = self.conf
+        normal = st[1] / st[0]
+        mask = st[2] / (self.n_patches * P)
+        eik = st[3] / (S * P)
+        return dict(loss=c["normal_weight"] * normal + c["mask_weight"] * mask + c["eikonal_weight"] * eik, normal=normal,
+                    mask=mask, eikonal=eik, n_samples=tot[0], n_ends=tot[1], overflow=tot[2], samples_per_ray=tot[0] / self.n_patches)
+
+    # -- measurement helpers ----------------------------------------------------------------------
+    def algorithmic_bytes(self, name: str, S: int, E: int) -> Optional[int]:
+        """HBM bytes one launch must move (SURVEY.md §8d per-unit figures x units), None if not modelled."""
+        m = self.model
+        M = P * (S + E)
+        na = m.n_active
+        if name == "snb_sdf_fwd_patch":      # write sdf (4 B) + kept features (4 B/level); read packed samples (12 B each)
+            return M * (4 + 4 * na) + S * 12
+        if name == "snb_sdf_bwd_patch":      # read features + seeds; table-gradient read-modify-write 8 corners x 8 B per level
+            return M * (4 * na + 4) + 2 * P * S * 4 + M * na * 8 * 8 * 2
+        if name == "snb_adam_step":          # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
+            return (2 * m.offsets[na]) * (16 + 16 + 2)
+        if name == "snb_march_visible":      # 40 B in per ray + 8 B per emitted sample (scratch)
+            return self.n_patches * 40 + S * 8
+        if name in ("snb_render_fwd", "snb_render_bwd"):
+            return P * S * (8 + (8 if name.endswith("bwd") else 0)) + S * 12 + self.n_patches * P * (36 + 12 + 12 + 4 + 16)
+        return None
+
+    def profile_kernels(self, steps: int = 20) -> dict:
+        """Per-entry-point device time (CUDA events on the launching stream) over `steps` real iterations."""
+        _lib.PROFILE = []
+        S_acc = E_acc = 0
+        try:
+            for _ in range(steps):
+                self.train_step()
+                tot = self.buf.totals.tolist()
+                S_acc += tot[0]
+                E_acc += tot[1]
+            torch.cuda.synchronize()
+            rec = _lib.PROFILE
+        finally:
+            _lib.PROFILE = None
+        agg: Dict[str, list] = {}
+        for name, e0, e1 in rec:
+            agg.setdefault(name, []).append(e0.elapsed_time(e1) * 1e3)
+        per_step = {k: sum(v) / steps for k, v in agg.items()}
+        total = sum(per_step.values())
+        out = {"us_per_step": {k: round(v, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+               "sum_us_per_step": round(total, 2), "avg_samples": S_acc / steps, "avg_ends": E_acc / steps,
+               "n_active": self.model.n_active}
+        S, E = int(S_acc / steps), int(E_acc / steps)
+        for name in sorted(per_step, key=lambda k: -per_step[k]):
+            nb = self.algorithmic_bytes(name, S, E)
+            if nb:
+                us = sum(agg[name]) / len(agg[name])
+                calls = len(agg[name]) / steps
+                if name == "snb_adam_step":  # two launches per step (small + table): attribute to the table sweep
+                    us = max(agg[name])
+                out["dominant"] = {"name": name, "us": us, "bytes": nb, "gbs": nb / (us * 1e-6) / 1e9, "share": per_step[name] / total,
+                                   "launches_per_step": calls}
+                break
+        return out
