@@ -216,7 +216,14 @@ def hashgrid_encode(x: torch.Tensor, params: torch.Tensor, spec: "_o.HashGridSpe
             feat = feat + wt[:, None] * tbl[off + _grid_index(size, res, pl)]
         outs.append(feat)
     out = torch.cat(outs, 1)
-    return _ste_half(out) if fp16 else out
+    if not fp16:
+        return out
+    if x.dtype == torch.float32:
+        # forward VALUE from the fp16-faithful C restatement (fp16 weights, fp16 fma chain), gradient of the
+        # fp32 expression above (straight-through, like the fp16 rounding itself)
+        exact = _o.hashgrid_fwd(spec, x.detach().numpy(), params.detach().numpy().astype(np.float16), n_active=n_active)
+        return out + (torch.from_numpy(exact.astype(np.float32)) - out.detach())
+    return _ste_half(out)
 
 
 def softplus100(x):
@@ -354,6 +361,8 @@ class NeuSRenderer:
             p1 = rays_o[pidx] + rays_d[pidx] * t1
             pos_all = torch.cat([p0, p1[dm]], 0)
         sdf_all = self.sdf_network(pos_all.reshape(-1, 3)).reshape(*pos_all.shape[:-1], 1)
+        if sdf_all.requires_grad:
+            sdf_all.retain_grad()  # tests compare d loss / d sdf with the fused kernels' seeds
         s0 = sdf_all[:S]
         s1 = _next_start_or_own_end(s0, sdf_all[S:], dm)
         inv_s = self.deviation_network.inv_s()
@@ -380,7 +389,7 @@ class NeuSRenderer:
         wsum = accumulate_along_rays_patch_based(w, pidx, n_patches=Np).reshape(Np, pH, pW, 1)
         comp = accumulate_along_rays_patch_based(w, pidx, values=grads.reshape(S, pH * pW, 3), n_patches=Np)
         return {"s_val": 1 / inv_s, "weight_sum": wsum, "gradients": grads, "comp_normal": comp.reshape(Np, pH, pW, 3),
-                "n_samples": S, "samples": (pidx, t0c, t1c), "sdf_start": s0, "sdf_end": s1, "alpha": alpha, "weights": w}
+                "n_samples": S, "samples": (pidx, t0c, t1c), "sdf_all": sdf_all, "diff_mask": dm, "sdf_start": s0, "sdf_end": s1, "alpha": alpha, "weights": w}
 
 
 def losses(out, true_normal, mask, normal_weight=1.0, mask_weight=1.0, eikonal_weight=1.0):
