@@ -236,6 +236,67 @@ int32_t snb_adam_step(int64_t n, float *param, float *grad, float *exp_avg, floa
                       float lr, float beta1, float beta2, float eps, int32_t step_count, float grad_scale,
                       snb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Device-side patch sampler and single-call training step: removes the
+ * per-iteration host work of Dataset.gen_random_patches / near_far_from_sphere
+ * (models/dataset_loader.py:223-297: ~30 ATen launches + a host np.random.choice + H2D) and of
+ * the per-kernel Python dispatch.
+ * ------------------------------------------------------------------------------------- */
+typedef struct snb_dataset { /* tensors Dataset.__init__ leaves on the device, models/dataset_loader.py:99-150 */
+    int32_t n_images, H, W, n_train;
+    const float *normals;        /* [n_images,H,W,3] world-space normals */
+    const float *masks;          /* [n_images,H,W] */
+    const float *intrinsics_inv; /* [n_images,4,4] */
+    const float *pose;           /* [n_images,4,4] camera-to-world */
+    const float *v_inverse;      /* [n_images,H,W,3,3] */
+    const int32_t *train_ids;    /* [n_train] view ids to sample from (exclude_views removed) */
+} snb_dataset;
+
+typedef struct snb_batch_out { /* writable twin of snb_patch_batch + stratified jitter */
+    float *rays_o, *rays_d, *plane_n, *near_, *far_, *v_inv, *normal_gt, *mask, *jitter;
+} snb_batch_out;
+
+/* Fills a batch of n_patches random 3x3 patches: centre pixel uniform in [1,W-3]x[1,H-3]
+ * (torch.randint(1, W-2), dataset_loader.py:244-245), view uniform over train_ids (:252), rays through the
+ * pixel centres (:262-267), near/far from the unit sphere (:279-297, NaN when missed), jitter ~ U[0,1).
+ * Counter-based RNG (Philox4x32-10) keyed by (seed, step): reproducible, no state. */
+int32_t snb_sample_patches(const snb_dataset *h_ds, int32_t n_patches, uint64_t seed, uint64_t step,
+                           const snb_batch_out *h_out, snb_stream_t stream);
+
+/* Fused occupancy update (NA/grid.py:197-239 with models/renderer.py:56-60 as occ_eval_fn), sync-free:
+ * warmup!=0: every cell; else every occupied cell (thinned to ~num_cells/4 if more are occupied) + num_cells/4
+ * uniform random cells.  occs_prev: scratch f32[num_cells]; workspace: >= 16 bytes. */
+int32_t snb_occgrid_update_fused(const snb_net *h_net, int32_t res_x, int32_t res_y, int32_t res_z, const float *roi,
+                                 int32_t warmup, float ema_decay, float occ_thre, uint64_t seed, uint64_t step,
+                                 float *occs, float *occs_prev, uint8_t *binary, void *workspace, snb_stream_t stream);
+
+typedef struct snb_train_ctx { /* everything one training iteration touches; all device pointers */
+    snb_patch_batch batch;
+    snb_samples samples;
+    snb_net net;              /* net.net = folded weights buffer, net.table_f16 = fp16 table */
+    int32_t n_levels;
+    int64_t small_pad;        /* floats in front of the hash table inside the flat buffers */
+    float *flat_param;        /* [small_pad + n_entries*2]  small | pad | table */
+    float *flat_grad, *exp_avg, *exp_avg_sq;
+    float *net_grad;          /* [SNB_NET_FLOATS] */
+    float *sdf;               /* [9*(capacity+end_capacity)] */
+    void *feats;              /* half2 [9*(capacity+end_capacity), n_levels] */
+    float *d_sdf0, *d_sdf1;   /* [9*capacity] */
+    float *comp, *wsum, *dcomp, *dwsum; /* [N,9,3] [N,9] */
+    float *stats;             /* [8] */
+    const float *jitter;      /* [N] or null */
+    const float *roi;         /* [6] */
+    const uint8_t *grid_binary;
+    int32_t res_x, res_y, res_z;
+} snb_train_ctx;
+
+/* prep_net -> march_visible -> compact -> sdf_fwd_patch -> render_fwd -> patch_loss -> render_bwd ->
+ * sdf_bwd_patch -> unfold_grads, all enqueued on `stream` by one host call (exp_runner.py:177-206). */
+int32_t snb_train_fwd_bwd(const snb_train_ctx *h_ctx, float step_size, float early_stop_eps, float normal_weight,
+                          float mask_weight, float eikonal_weight, snb_stream_t stream);
+/* Adam over the MLP/variance parameters and the active levels of the table (exp_runner.py:207) */
+int32_t snb_train_optim(const snb_train_ctx *h_ctx, float lr, int32_t step_count, float grad_scale, snb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

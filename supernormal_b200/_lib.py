@@ -25,7 +25,7 @@ class HashGridMeta(C.Structure):
                 ("scales", C.c_float * SNB_MAX_LEVELS), ("resolutions", C.c_uint32 * SNB_MAX_LEVELS)]
 
 
-_CTYPE = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "float": C.c_float,
+_CTYPE = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "float": C.c_float,
           "snb_stream_t": C.c_void_p}
 
 
@@ -86,7 +86,8 @@ def stream() -> int:
 
 LAUNCH_COUNT = 0
 # kernels launched per entry point (memsets not counted)
-KERNELS = {"snb_occgrid_binarize": 2, "snb_compact_samples": 2, "snb_max_i64": 2}
+KERNELS = {"snb_occgrid_binarize": 2, "snb_compact_samples": 2, "snb_max_i64": 2, "snb_train_fwd_bwd": 10,
+           "snb_train_optim": 2, "snb_occgrid_update_fused": 3}
 
 
 PROFILE = None  # set to a list to record (name, start_event, end_event) around every call

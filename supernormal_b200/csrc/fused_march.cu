@@ -66,6 +66,25 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
     float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 
     while (t_mid < far) {
+        {   // empty space: warp-uniform probe + DDA skip (no speculation, no SDF work)
+            float cx = __fmaf_rn(t_mid, dx, ox), cy = __fmaf_rn(t_mid, dy, oy), cz = __fmaf_rn(t_mid, dz, oz);
+            if (!occ_at(cx, cy, cz, rmin, rmax, res, grid)) {
+                float tx = axis_dist_(cx, dx, ix, rmin[0], rmax[0], res.x);
+                float ty = axis_dist_(cy, dy, iy, rmin[1], rmax[1], res.y);
+                float tz = axis_dist_(cz, dz, iz, rmin[2], rmax[2], res.z);
+                float t_target = fminf(__fadd_rn(t_mid, fmaxf(fminf(fminf(tx, ty), tz), 0.0f)), far);
+                float t = t_mid;
+                do {
+                    t = __fadd_rn(t, step);
+                } while (t < t_target);
+                t_mid = t;
+                float dt = calc_dt_(t_mid, 0.f, step);
+                t0 = __fmaf_rn(dt, -0.5f, t_mid);
+                t1 = __fmaf_rn(dt, 0.5f, t_mid);
+                chain_open = false;
+                continue;
+            }
+        }
         float l0 = t0, l1 = t1;
         for (int s = 0; s < lane; ++s) {
             l0 = l1;

@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
         float hact[kH];
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
-            float z = dz[h];
-            hact[h] = dsdf * softplus100(z);                        // -> dW1
-            dz[h] = dsdf * s_net[kOffW1 + h] * softplus100_grad(z);  // -> dz
+            float sp, sg;
+            softplus100_both(dz[h], sp, sg);
+            hact[h] = dsdf * sp;                       // -> dW1
+            dz[h] = dsdf * s_net[kOffW1 + h] * sg;     // -> dz
         }
         float4 *dzrow = reinterpret_cast<float4 *>(s_dz + tid * kDzStride);
 #pragma unroll

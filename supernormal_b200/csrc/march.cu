@@ -75,6 +75,27 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *
     float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 
     while (t_mid < far) {  // warp-uniform state
+        // Empty space: probe only the current candidate (warp-uniform, broadcast load) and DDA-skip; the
+        // 32-wide speculation below is only worth its cost once a sample has been found.
+        {
+            float cx = __fmaf_rn(t_mid, dx, ox), cy = __fmaf_rn(t_mid, dy, oy), cz = __fmaf_rn(t_mid, dz, oz);
+            if (!occupied_at(cx, cy, cz, rmin, rmax, a.res, a.grid)) {
+                float tx = axis_dist(cx, dx, ix, rmin[0], rmax[0], a.res.x);
+                float ty = axis_dist(cy, dy, iy, rmin[1], rmax[1], a.res.y);
+                float tz = axis_dist(cz, dz, iz, rmin[2], rmax[2], a.res.z);
+                float dist = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+                float t_target = fminf(__fadd_rn(t_mid, dist), far);
+                float t = t_mid;
+                do {
+                    t = __fadd_rn(t, dt_min);
+                } while (t < t_target);
+                t_mid = t;
+                float dt = calc_dt(t_mid, a.cone, dt_min);
+                t0 = __fmaf_rn(dt, -0.5f, t_mid);
+                t1 = __fmaf_rn(dt, 0.5f, t_mid);
+                continue;
+            }
+        }
         // lane l: state after l consecutive occupied samples
         float l0 = t0, l1 = t1;
         for (int s = 0; s < lane; ++s) {

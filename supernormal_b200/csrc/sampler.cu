@@ -1,0 +1,200 @@
+// sampler.cu -- device-side random patch sampler (models/dataset_loader.py:223-297) and the single-call
+// training step that enqueues the whole iteration from C++ (no per-kernel Python dispatch).
+#include "sdf_core.cuh"
+
+namespace snb {
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: ctr = (step lo, step hi, index, stream), key = seed
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }  // [0,1), 24 bits like torch.rand
+
+__global__ void __launch_bounds__(256) sample_patches_kernel(snb_dataset ds, int n_patches, uint64_t seed, uint64_t step,
+                                                             snb_batch_out out) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_patches * SNB_PATCH) return;
+    int i = tid / SNB_PATCH, k = tid % SNB_PATCH;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)i, 0x5a4dce11u),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    int cx = 1 + (int)(r.x % (uint32_t)(ds.W - 3));   // randint(low=1, high=W-2)
+    int cy = 1 + (int)(r.y % (uint32_t)(ds.H - 3));
+    int view = __ldg(ds.train_ids + (r.z % (uint32_t)ds.n_train));
+    int px = cx + (k % 3) - 1, py = cy + (k / 3) - 1;
+    const float *Ki = ds.intrinsics_inv + view * 16, *Pm = ds.pose + view * 16;
+    float fx = (float)px, fy = (float)py;
+    float p[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = __ldg(Ki + 4 * a) * fx + __ldg(Ki + 4 * a + 1) * fy + __ldg(Ki + 4 * a + 2);
+    float inv = 1.f / sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    p[0] *= inv; p[1] *= inv; p[2] *= inv;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) d[a] = __ldg(Pm + 4 * a) * p[0] + __ldg(Pm + 4 * a + 1) * p[1] + __ldg(Pm + 4 * a + 2) * p[2];
+    float o[3] = {__ldg(Pm + 3), __ldg(Pm + 7), __ldg(Pm + 11)};
+    int64_t rk = (int64_t)i * SNB_PATCH + k;
+    out.rays_d[3 * rk] = d[0]; out.rays_d[3 * rk + 1] = d[1]; out.rays_d[3 * rk + 2] = d[2];
+    int64_t pix = ((int64_t)view * ds.H + py) * ds.W + px;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) out.normal_gt[3 * rk + a] = __ldg(ds.normals + 3 * pix + a);
+    out.mask[rk] = __ldg(ds.masks + pix);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) out.v_inv[9 * rk + a] = __ldg(ds.v_inverse + 9 * pix + a);
+    if (k == SNB_PATCH / 2) {
+        out.rays_o[3 * i] = o[0]; out.rays_o[3 * i + 1] = o[1]; out.rays_o[3 * i + 2] = o[2];
+        out.plane_n[3 * i] = __ldg(Pm + 2); out.plane_n[3 * i + 1] = __ldg(Pm + 6); out.plane_n[3 * i + 2] = __ldg(Pm + 10);
+        // near_far_from_sphere, models/dataset_loader.py:279-297
+        float a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        float b = 2.0f * (o[0] * d[0] + o[1] * d[1] + o[2] * d[2]);
+        float c = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] - 1.0f;
+        float mid = 0.5f * (-b) / a;
+        float root = sqrtf(b * b - 4.f * a * c) / (2.f * a);  // NaN if the ray misses the unit sphere
+        out.near_[i] = mid - root;
+        out.far_[i] = mid + root;
+        if (out.jitter) out.jitter[i] = u01(r.w);
+    }
+}
+
+// ---- fused occupancy update --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) occgrid_update_kernel(snb_net net, int3 res, const float *__restrict__ roi, int warmup,
+                                                             float decay, uint64_t seed, uint64_t step, float *__restrict__ occs,
+                                                             const float *__restrict__ occs_prev, const uint8_t *__restrict__ binary,
+                                                             const unsigned long long *__restrict__ ws) {
+    __shared__ __align__(16) float s_net[kNetFloats];
+    load_net_to_smem(s_net, net.net);
+    const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
+    const int64_t num_cells = (int64_t)res.x * res.y * res.z;
+    const int64_t n_uniform = warmup ? 0 : num_cells / 4;
+    const int64_t total = num_cells + n_uniform;
+    const uint2 key = make_uint2((uint32_t)seed ^ 0x0cc61d00u, (uint32_t)(seed >> 32));
+    // thinning probability of occupied cells so that ~num_cells/4 of them are re-evaluated (NA/grid.py:187-192)
+    float thin = 1.f;
+    if (!warmup) {
+        unsigned long long n_occ = ws[1];
+        if (n_occ > (unsigned long long)(num_cells / 4)) thin = (float)(num_cells / 4) / (float)n_occ;
+    }
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+        uint4 r = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)w, (uint32_t)(w >> 32) ^ 0x77u), key);
+        int64_t c;
+        if (w < num_cells) {
+            c = w;
+            if (!warmup) {
+                if (!binary[c]) continue;
+                if (thin < 1.f) {
+                    uint4 r2 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)w, 0x1234567u), key);
+                    if (u01(r2.x) >= thin) continue;
+                }
+            }
+        } else {
+            c = (int64_t)(r.w % (uint32_t)num_cells);
+        }
+        int cz = (int)(c % res.z), cy = (int)((c / res.z) % res.y), cx = (int)(c / ((int64_t)res.z * res.y));
+        int cc[3] = {cx, cy, cz}, rr[3] = {res.x, res.y, res.z};
+        float rnd[3] = {u01(r.x), u01(r.y), u01(r.z)}, x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float u = __fdiv_rn(__fadd_rn((float)cc[d], rnd[d]), (float)rr[d]);
+            float lo = __ldg(roi + d), hi = __ldg(roi + 3 + d);
+            x[d] = __fmaf_rn(u, __fsub_rn(hi, lo), lo);
+        }
+        float s = sdf_point<false>(x[0], x[1], x[2], table, net.meta, net.n_active, s_net, nullptr);
+        occs[c] = fmaxf(__fmul_rn(occs_prev[c], decay), sigmoidf_(-s * 80.f));
+    }
+}
+
+__global__ void occgrid_sum2_kernel(int64_t n, const float *__restrict__ occs, double *__restrict__ sum) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += occs[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sum, s);
+}
+__global__ void occgrid_threshold2_kernel(int64_t n, const float *__restrict__ occs, const double *__restrict__ sum, float thre,
+                                          uint8_t *__restrict__ binary, unsigned long long *__restrict__ count) {
+    float th = fminf((float)(*sum / (double)n), thre);
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        bool b = occs[i] > th;
+        binary[i] = b ? 1 : 0;
+        c += b;
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+}  // namespace snb
+using namespace snb;
+
+extern "C" int32_t snb_sample_patches(const snb_dataset *ds, int32_t n_patches, uint64_t seed, uint64_t step, const snb_batch_out *out,
+                                      snb_stream_t stream) {
+    SNB_REQUIRE(ds && out, SNB_ERR_NULL, "sample_patches: null struct");
+    SNB_REQUIRE(n_patches >= 0 && ds->W > 3 && ds->H > 3 && ds->n_train > 0 && ds->n_images > 0, SNB_ERR_ARG, "sample_patches: bad sizes");
+    if (n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(ds->normals && ds->masks && ds->intrinsics_inv && ds->pose && ds->v_inverse && ds->train_ids, SNB_ERR_NULL, "sample_patches: null dataset tensor");
+    SNB_REQUIRE(out->rays_o && out->rays_d && out->plane_n && out->near_ && out->far_ && out->v_inv && out->normal_gt && out->mask, SNB_ERR_NULL,
+                "sample_patches: null output");
+    sample_patches_kernel<<<(unsigned)cdiv((int64_t)n_patches * SNB_PATCH, 256), 256, 0, S(stream)>>>(*ds, n_patches, seed, step, *out);
+    SNB_LAUNCH_CHECK("sample_patches");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_occgrid_update_fused(const snb_net *net, int32_t rx, int32_t ry, int32_t rz, const float *roi, int32_t warmup,
+                                            float ema_decay, float occ_thre, uint64_t seed, uint64_t step, float *occs, float *occs_prev,
+                                            uint8_t *binary, void *workspace, snb_stream_t stream) {
+    SNB_REQUIRE(net && net->table_f16 && net->net, SNB_ERR_NULL, "occgrid_update_fused: null net");
+    SNB_REQUIRE(rx > 0 && ry > 0 && rz > 0, SNB_ERR_ARG, "occgrid_update_fused: bad resolution");
+    SNB_REQUIRE(roi && occs && occs_prev && binary && workspace, SNB_ERR_NULL, "occgrid_update_fused: null buffer");
+    SNB_REQUIRE(aligned(workspace, 8) && aligned(net->net, 16), SNB_ERR_ALIGN, "occgrid_update_fused: misaligned workspace/net");
+    const int64_t n = (int64_t)rx * ry * rz;
+    cudaMemcpyAsync(occs_prev, occs, sizeof(float) * n, cudaMemcpyDeviceToDevice, S(stream));
+    occgrid_update_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*net, make_int3(rx, ry, rz), roi, warmup, ema_decay, seed, step, occs, occs_prev,
+                                                            binary, (const unsigned long long *)workspace);
+    cudaMemsetAsync(workspace, 0, 16, S(stream));
+    occgrid_sum2_kernel<<<kNumSMs * 4, 256, 0, S(stream)>>>(n, occs, (double *)workspace);
+    occgrid_threshold2_kernel<<<kNumSMs * 4, 256, 0, S(stream)>>>(n, occs, (const double *)workspace, occ_thre, binary,
+                                                                 (unsigned long long *)workspace + 1);
+    SNB_LAUNCH_CHECK("occgrid_update_fused");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_train_fwd_bwd(const snb_train_ctx *c, float step_size, float early_stop_eps, float normal_weight, float mask_weight,
+                                     float eikonal_weight, snb_stream_t stream) {
+    SNB_REQUIRE(c, SNB_ERR_NULL, "train_fwd_bwd: null ctx");
+    SNB_REQUIRE(c->flat_param && c->flat_grad && c->net_grad && c->stats && c->sdf && c->feats && c->d_sdf0 && c->d_sdf1 && c->comp && c->wsum &&
+                    c->dcomp && c->dwsum, SNB_ERR_NULL, "train_fwd_bwd: null buffer");
+    const int n = c->batch.n_patches;
+    int32_t rc;
+    float *net_w = const_cast<float *>(c->net.net);
+    if ((rc = snb_prep_net(c->n_levels, c->flat_param, net_w, n * SNB_PATCH, c->batch.mask, c->stats, stream))) return rc;
+    if ((rc = snb_march_visible(&c->batch, &c->net, c->roi, c->res_x, c->res_y, c->res_z, c->grid_binary, step_size, c->jitter, early_stop_eps,
+                                &c->samples, stream))) return rc;
+    if ((rc = snb_compact_samples(n, &c->samples, stream))) return rc;
+    if ((rc = snb_sdf_fwd_patch(&c->batch, &c->net, &c->samples, c->sdf, c->feats, stream))) return rc;
+    if ((rc = snb_render_fwd(&c->batch, &c->net, &c->samples, c->sdf, c->comp, c->wsum, nullptr, nullptr, c->stats, stream))) return rc;
+    if ((rc = snb_patch_loss(&c->batch, c->comp, c->wsum, normal_weight, mask_weight, c->stats, c->dcomp, c->dwsum, stream))) return rc;
+    if ((rc = snb_render_bwd(&c->batch, &c->net, &c->samples, c->sdf, c->comp, c->wsum, c->dcomp, c->dwsum, nullptr, eikonal_weight, c->d_sdf0,
+                             c->d_sdf1, c->stats, stream))) return rc;
+    cudaMemsetAsync(c->net_grad, 0, sizeof(float) * SNB_NET_FLOATS, S(stream));
+    if ((rc = snb_sdf_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad, stream)))
+        return rc;
+    return snb_unfold_grads(c->n_levels, c->flat_param, c->net_grad, c->stats, c->flat_grad, stream);
+}
+
+extern "C" int32_t snb_train_optim(const snb_train_ctx *c, float lr, int32_t step_count, float grad_scale, snb_stream_t stream) {
+    SNB_REQUIRE(c, SNB_ERR_NULL, "train_optim: null ctx");
+    SNB_REQUIRE(c->flat_param && c->flat_grad && c->exp_avg && c->exp_avg_sq, SNB_ERR_NULL, "train_optim: null buffer");
+    int32_t rc = snb_adam_step(c->small_pad, c->flat_param, c->flat_grad, c->exp_avg, c->exp_avg_sq, nullptr, lr, 0.9f, 0.999f, 1e-8f, step_count,
+                               grad_scale, stream);
+    if (rc) return rc;
+    // levels >= n_active have exactly zero gradient and Adam state: skipping them is exact (no weight decay)
+    const int64_t n_live = 2 * (int64_t)c->net.meta.offsets[c->net.n_active];
+    const int64_t o = c->small_pad;
+    return snb_adam_step(n_live, c->flat_param + o, c->flat_grad + o, c->exp_avg + o, c->exp_avg_sq + o, const_cast<void *>(c->net.table_f16), lr,
+                         0.9f, 0.999f, 1e-8f, step_count, grad_scale, stream);
+}

@@ -42,6 +42,25 @@ class SnbSamples(C.Structure):
                 ("scratch_t0", C.c_void_p), ("scratch_t1", C.c_void_p)]
 
 
+class SnbDataset(C.Structure):
+    _fields_ = [("n_images", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_train", C.c_int32), ("normals", C.c_void_p),
+                ("masks", C.c_void_p), ("intrinsics_inv", C.c_void_p), ("pose", C.c_void_p), ("v_inverse", C.c_void_p),
+                ("train_ids", C.c_void_p)]
+
+
+class SnbBatchOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rays_o", "rays_d", "plane_n", "near_", "far_", "v_inv", "normal_gt", "mask", "jitter")]
+
+
+class SnbTrainCtx(C.Structure):
+    _fields_ = [("batch", SnbPatchBatch), ("samples", SnbSamples), ("net", SnbNet), ("n_levels", C.c_int32), ("small_pad", C.c_int64),
+                ("flat_param", C.c_void_p), ("flat_grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("net_grad", C.c_void_p), ("sdf", C.c_void_p), ("feats", C.c_void_p), ("d_sdf0", C.c_void_p), ("d_sdf1", C.c_void_p),
+                ("comp", C.c_void_p), ("wsum", C.c_void_p), ("dcomp", C.c_void_p), ("dwsum", C.c_void_p), ("stats", C.c_void_p),
+                ("jitter", C.c_void_p), ("roi", C.c_void_p), ("grid_binary", C.c_void_p), ("res_x", C.c_int32), ("res_y", C.c_int32),
+                ("res_z", C.c_int32)]
+
+
 class SDFModel:
     """Parameters of SDFNetwork (models/fields.py:7-99, shipped configuration: one 64-wide hidden layer,
     weight-norm, Softplus(beta=100), input_concat, geometric init) + SingleVarianceNetwork
@@ -213,6 +232,26 @@ class FusedTrainer:
         self.buf = SampleBuffers(self.n_patches, samples_per_ray_cap, stride, self.model.n_levels, self.device)
         from .nerfacc_api import OccupancyGrid
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
+        self.seed = seed + 7919 * rank
+        self.fused_host = True        # one C-ABI call per phase instead of one per kernel
+        self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
+        dv = self.device
+        n, Pn = self.n_patches, P
+        self.own_batch = dict(rays_o=torch.zeros(n, 3, device=dv), rays_d=torch.zeros(n, Pn, 3, device=dv), plane_n=torch.zeros(n, 3, device=dv),
+                              near=torch.zeros(n, device=dv), far=torch.zeros(n, device=dv), v_inv=torch.zeros(n, Pn, 9, device=dv),
+                              normal_gt=torch.zeros(n, Pn, 3, device=dv), mask=torch.zeros(n, Pn, device=dv))
+        self.own_jitter = torch.zeros(n, device=dv)
+        self.train_ids = torch.tensor(dataset.train_images, dtype=torch.int32, device=dv)
+        self.ds_struct = SnbDataset(dataset.n_images, dataset.H, dataset.W, len(dataset.train_images), dataset.normals.data_ptr(),
+                                    dataset.masks.data_ptr(), dataset.intrinsics_all_inv.data_ptr(), dataset.pose_all.data_ptr(),
+                                    dataset.V_inverse_all.data_ptr(), self.train_ids.data_ptr())
+        for t in (dataset.normals, dataset.masks, dataset.intrinsics_all_inv, dataset.pose_all, dataset.V_inverse_all):
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.device == dv
+        ob = self.own_batch
+        self.out_struct = SnbBatchOut(*[ob[k].data_ptr() for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")],
+                                      self.own_jitter.data_ptr())
+        self.occs_prev = torch.zeros(self.grid.num_cells, device=dv)
+        self.occ_ws = torch.zeros(2, dtype=torch.float64, device=dv)
         self.iter_step = 0
         self.lr = float(conf["learning_rate"])  # Adam's constructor value is what step 0 uses (exp_runner.py:97,210)
         self.gen = torch.Generator(device=self.device).manual_seed(seed + rank)
@@ -233,7 +272,30 @@ class FusedTrainer:
     def update_occupancy(self, it: int):
         rm = self.conf["ray_marching"]
         self.model.prep()
-        self.grid._update(step=it, occ_eval_fn=lambda x: self.model.sdf(x, mode=1), occ_thre=rm["occ_threshold"])
+        if self.fused_host:
+            net = self.model.net_struct()
+            binary = self.grid._binary
+            call("snb_occgrid_update_fused", C.byref(net), *self.grid._res, ptr(self.grid.roi_aabb), int(it < 256), 0.95,
+                 float(rm["occ_threshold"]), self.seed, it, ptr(self.grid.occs), ptr(self.occs_prev), ptr(binary.view(torch.uint8)),
+                 ptr(self.occ_ws))
+        else:
+            self.grid._update(step=it, occ_eval_fn=lambda x: self.model.sdf(x, mode=1), occ_thre=rm["occ_threshold"])
+
+    def sample_batch_device(self, it: int):
+        """Device-side sampler: fills self.own_batch / self.own_jitter in one launch."""
+        call("snb_sample_patches", C.byref(self.ds_struct), self.n_patches, self.seed, it, C.byref(self.out_struct))
+        return self.own_batch, self.own_jitter
+
+    def _ctx(self, batch: dict, jitter) -> SnbTrainCtx:
+        m, b = self.model, self.buf
+        bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"],
+                               batch["v_inv"], batch["normal_gt"], batch["mask"])
+        g = self.grid
+        return SnbTrainCtx(bs, b.struct, m.net_struct(), m.n_levels, SMALL_PAD, m.flat.data_ptr(), m.grad.data_ptr(),
+                           m.exp_avg.data_ptr(), m.exp_avg_sq.data_ptr(), m.net_grad.data_ptr(), b.sdf.data_ptr(), b.feats.data_ptr(),
+                           b.d_sdf0.data_ptr(), b.d_sdf1.data_ptr(), b.comp.data_ptr(), b.wsum.data_ptr(), b.dcomp.data_ptr(),
+                           b.dwsum.data_ptr(), b.stats.data_ptr(), 0 if jitter is None else jitter.data_ptr(), g.roi_aabb.data_ptr(),
+                           g.binary.data_ptr(), *g._res)
 
     def sample_batch(self):
         c = self.conf
@@ -248,9 +310,14 @@ class FusedTrainer:
         """march -> sdf -> render -> loss -> backward; leaves gradients in model.grad (small + table)."""
         m, b = self.model, self.buf
         c = self.conf
+        self.last_batch = batch
+        if self.fused_host:
+            ctx = self._ctx(batch, jitter)
+            call("snb_train_fwd_bwd", C.byref(ctx), float(step_size), 1e-8, float(c["normal_weight"]), float(c["mask_weight"]),
+                 float(c["eikonal_weight"]))
+            return
         bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"],
                                batch["v_inv"], batch["normal_gt"], batch["mask"])
-        self.last_batch = batch
         m.prep(batch["mask"], b.stats)
         net = m.net_struct()
         rb, rn, rs = C.byref(bs), C.byref(net), C.byref(b.struct)
@@ -277,6 +344,10 @@ class FusedTrainer:
             dist.all_reduce(m.grad[:n_live])
             gscale = 1.0 / self.world_size
         t = self.iter_step + 1
+        if self.fused_host:
+            ctx = self._ctx(self.last_batch, None)
+            call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)
+            return
         call("snb_adam_step", SMALL_PAD, ptr(m.flat), ptr(m.grad), ptr(m.exp_avg), ptr(m.exp_avg_sq), None,
              self.lr, 0.9, 0.999, 1e-8, t, gscale)
         nt = n_live - SMALL_PAD
@@ -291,6 +362,8 @@ class FusedTrainer:
             self.update_occupancy(it)
         if it % c["increase_bindwidth_every"] == 0:
             self.model.n_active = min(self.model.n_active + 1, self.model.n_levels)
+        if batch is None and self.device_sampler:
+            batch, jitter = self.sample_batch_device(it)
         if batch is None:
             batch = self.sample_batch()
         if jitter is None:
@@ -334,6 +407,7 @@ class FusedTrainer:
         """Per-entry-point device time (CUDA events on the launching stream) over `steps` real iterations."""
         _lib.PROFILE = []
         S_acc = E_acc = 0
+        saved, self.fused_host = self.fused_host, False   # per-kernel entry points so each launch can be bracketed
         try:
             for _ in range(steps):
                 self.train_step()
@@ -344,6 +418,7 @@ class FusedTrainer:
             rec = _lib.PROFILE
         finally:
             _lib.PROFILE = None
+            self.fused_host = saved
         agg: Dict[str, list] = {}
         for name, e0, e1 in rec:
             agg.setdefault(name, []).append(e0.elapsed_time(e1) * 1e3)
