@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 make -s -C oracle
-python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^E |Error" | head -40
+python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^E  |Error|^FAILED" | head -60
 python bench.py --steps ${STEPS:-400} --warmup ${WARMUP:-20} ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench.json
 if [ "${NCU:-1}" = "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-600} -c ${NCU_COUNT:-300} --csv --log-file gpurun_out/launches.csv \

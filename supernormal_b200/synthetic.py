@@ -67,7 +67,7 @@ class SyntheticDataset:
             poses.append(_look_at_pose(eye))
         dev = self.device
         self.intrinsics_all = torch.from_numpy(np.stack([K] * s.n_views)).float().to(dev)
-        self.intrinsics_all_inv = torch.inverse(self.intrinsics_all)
+        self.intrinsics_all_inv = torch.inverse(self.intrinsics_all).contiguous()
         self.pose_all = torch.from_numpy(np.stack(poses)).float().to(dev)
         self.focal_length = self.intrinsics_all[0][0, 0]
 
@@ -95,10 +95,10 @@ class SyntheticDataset:
                 right = R[:, 0].expand_as(d)
                 down = R[:, 1].expand_as(d)
                 V = torch.stack([d, right, down], dim=-2)  # rows: ray dir, cam right, cam down
-                vinv.append(torch.inverse(V))
+                vinv.append(torch.inverse(V).contiguous())
         self.normals = torch.stack(normals)           # [n,H,W,3]
         self.masks = torch.stack(masks)               # [n,H,W]
-        self.V_inverse_all = torch.stack(vinv) if with_v_inverse else None  # [n,H,W,3,3]
+        self.V_inverse_all = torch.stack(vinv).contiguous() if with_v_inverse else None  # [n,H,W,3,3]
         self.object_bbox_min = np.array([-1.0, -1.0, -1.0])
         self.object_bbox_max = np.array([1.0, 1.0, 1.0])
 

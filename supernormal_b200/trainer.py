@@ -242,11 +242,11 @@ class FusedTrainer:
                               normal_gt=torch.zeros(n, Pn, 3, device=dv), mask=torch.zeros(n, Pn, device=dv))
         self.own_jitter = torch.zeros(n, device=dv)
         self.train_ids = torch.tensor(dataset.train_images, dtype=torch.int32, device=dv)
-        self.ds_struct = SnbDataset(dataset.n_images, dataset.H, dataset.W, len(dataset.train_images), dataset.normals.data_ptr(),
-                                    dataset.masks.data_ptr(), dataset.intrinsics_all_inv.data_ptr(), dataset.pose_all.data_ptr(),
-                                    dataset.V_inverse_all.data_ptr(), self.train_ids.data_ptr())
-        for t in (dataset.normals, dataset.masks, dataset.intrinsics_all_inv, dataset.pose_all, dataset.V_inverse_all):
-            assert t.is_contiguous() and t.dtype == torch.float32 and t.device == dv
+        # the C ABI reads dense fp32 tensors (torch.inverse may hand back column-major batches)
+        self._ds_tensors = [t.to(dv, torch.float32).contiguous() for t in (dataset.normals, dataset.masks, dataset.intrinsics_all_inv,
+                                                                            dataset.pose_all, dataset.V_inverse_all)]
+        self.ds_struct = SnbDataset(dataset.n_images, dataset.H, dataset.W, len(dataset.train_images),
+                                    *[t.data_ptr() for t in self._ds_tensors], self.train_ids.data_ptr())
         ob = self.own_batch
         self.out_struct = SnbBatchOut(*[ob[k].data_ptr() for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")],
                                       self.own_jitter.data_ptr())
