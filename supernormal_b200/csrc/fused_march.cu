@@ -9,30 +9,10 @@
 // HBM round trip), multiplies T serially, and stops marching the moment T < eps: late in training
 // this evaluates ~S instead of ~S0 >> S points.  Samples go to a per-ray scratch; a device scan and
 // a copy kernel pack them by patch with no host round trip.
+#include "march_common.cuh"
 #include "sdf_core.cuh"
 
 namespace snb {
-
-__device__ __forceinline__ float calc_dt_(float t, float cone, float dt_min) {
-    return fmaxf(dt_min, fminf(__fmul_rn(t, cone), 1e10f));
-}
-__device__ __forceinline__ bool occ_at(float x, float y, float z, const float *rmin, const float *rmax, int3 res,
-                                       const uint8_t *__restrict__ grid) {
-    if (x < rmin[0] || x > rmax[0] || y < rmin[1] || y > rmax[1] || z < rmin[2] || z > rmax[2]) return false;
-    float ux = __fdiv_rn(__fsub_rn(x, rmin[0]), __fsub_rn(rmax[0], rmin[0]));
-    float uy = __fdiv_rn(__fsub_rn(y, rmin[1]), __fsub_rn(rmax[1], rmin[1]));
-    float uz = __fdiv_rn(__fsub_rn(z, rmin[2]), __fsub_rn(rmax[2], rmin[2]));
-    int ix = min(max(__float2int_rz(__fmul_rn(ux, (float)res.x)), 0), res.x - 1);
-    int iy = min(max(__float2int_rz(__fmul_rn(uy, (float)res.y)), 0), res.y - 1);
-    int iz = min(max(__float2int_rz(__fmul_rn(uz, (float)res.z)), 0), res.z - 1);
-    return __ldg(grid + ((ix * res.y + iy) * res.z + iz)) != 0;
-}
-__device__ __forceinline__ float axis_dist_(float p, float dir, float inv_dir, float rmin, float rmax, int r) {
-    float rf = (float)r, ext = __fsub_rn(rmax, rmin);
-    float u = __fdiv_rn(__fsub_rn(p, rmin), ext);
-    float fl = floorf(__fmaf_rn(copysignf(1.0f, dir), 0.5f, __fmaf_rn(rf, u, 0.5f)));
-    return __fmul_rn(__fdiv_rn(__fmul_rn(__fmaf_rn(rf, -u, fl), inv_dir), rf), ext);
-}
 
 __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, snb_net net, const float *__restrict__ roi,
                                                             int3 res, const uint8_t *__restrict__ grid, float step,
@@ -45,15 +25,14 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const float inv_s = s_net[kOffInvS];
 
-    const float ox = __ldg(b.rays_o + 3 * ray), oy = __ldg(b.rays_o + 3 * ray + 1), oz = __ldg(b.rays_o + 3 * ray + 2);
+    const RoiCtx rc = make_roi_ctx(roi, res);
+    const float o[3] = {__ldg(b.rays_o + 3 * ray), __ldg(b.rays_o + 3 * ray + 1), __ldg(b.rays_o + 3 * ray + 2)};
     const float *dc = b.rays_d + ((int64_t)ray * SNB_PATCH + SNB_PATCH / 2) * 3;  // centre ray of the patch
-    const float dx = __ldg(dc), dy = __ldg(dc + 1), dz = __ldg(dc + 2);
-    const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+    const float d[3] = {__ldg(dc), __ldg(dc + 1), __ldg(dc + 2)};
+    const float inv_d[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
     float near = __ldg(b.near_ + ray);
     const float far = __ldg(b.far_ + ray);
     if (jitter) near = __fadd_rn(near, __fmul_rn(__ldg(jitter + ray), step));  // NA/ray_marching.py:158
-    float rmin[3] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2)};
-    float rmax[3] = {__ldg(roi + 3), __ldg(roi + 4), __ldg(roi + 5)};
 
     float *sc0 = sm.scratch_t0 + (int64_t)ray * sm.scratch_stride;
     float *sc1 = sm.scratch_t1 + (int64_t)ray * sm.scratch_stride;
@@ -62,23 +41,15 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
     bool chain_open = false, overflow = false;
     float T = 1.f;
     float t0 = near;
-    float t1 = __fadd_rn(t0, calc_dt_(t0, 0.f, step));
+    float t1 = __fadd_rn(t0, march_dt(t0, 0.f, step));
     float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 
     while (t_mid < far) {
         {   // empty space: warp-uniform probe + DDA skip (no speculation, no SDF work)
-            float cx = __fmaf_rn(t_mid, dx, ox), cy = __fmaf_rn(t_mid, dy, oy), cz = __fmaf_rn(t_mid, dz, oz);
-            if (!occ_at(cx, cy, cz, rmin, rmax, res, grid)) {
-                float tx = axis_dist_(cx, dx, ix, rmin[0], rmax[0], res.x);
-                float ty = axis_dist_(cy, dy, iy, rmin[1], rmax[1], res.y);
-                float tz = axis_dist_(cz, dz, iz, rmin[2], rmax[2], res.z);
-                float t_target = fminf(__fadd_rn(t_mid, fmaxf(fminf(fminf(tx, ty), tz), 0.0f)), far);
-                float t = t_mid;
-                do {
-                    t = __fadd_rn(t, step);
-                } while (t < t_target);
-                t_mid = t;
-                float dt = calc_dt_(t_mid, 0.f, step);
+            float cx = __fmaf_rn(t_mid, d[0], o[0]), cy = __fmaf_rn(t_mid, d[1], o[1]), cz = __fmaf_rn(t_mid, d[2], o[2]);
+            if (!march_occupied(rc, cx, cy, cz, grid)) {
+                t_mid = march_skip(rc, t_mid, step, cx, cy, cz, d, inv_d, far);
+                float dt = march_dt(t_mid, 0.f, step);
                 t0 = __fmaf_rn(dt, -0.5f, t_mid);
                 t1 = __fmaf_rn(dt, 0.5f, t_mid);
                 chain_open = false;
@@ -88,12 +59,12 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
         float l0 = t0, l1 = t1;
         for (int s = 0; s < lane; ++s) {
             l0 = l1;
-            l1 = __fadd_rn(l0, calc_dt_(l0, 0.f, step));
+            l1 = __fadd_rn(l0, march_dt(l0, 0.f, step));
         }
         float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
-        float px = __fmaf_rn(lm, dx, ox), py = __fmaf_rn(lm, dy, oy), pz = __fmaf_rn(lm, dz, oz);
+        float px = __fmaf_rn(lm, d[0], o[0]), py = __fmaf_rn(lm, d[1], o[1]), pz = __fmaf_rn(lm, d[2], o[2]);
         bool in_range = lm < far;
-        bool occ = (lane < 31) && in_range && occ_at(px, py, pz, rmin, rmax, res, grid);
+        bool occ = (lane < 31) && in_range && march_occupied(rc, px, py, pz, grid);
         unsigned stop = ~__ballot_sync(0xffffffffu, occ);  // bit 31 always set: lane 31 only evaluates an end point
         int f = __ffs(stop) - 1;                           // lanes [0,f) are samples, f <= 31
         bool ray_done = false;
@@ -102,8 +73,8 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
             // reference builds them: t_origins + t_dirs * t (models/renderer.py:84-86), separately rounded
             float sdf = 0.f;
             if (lane <= f)
-                sdf = sdf_point<false>(__fadd_rn(ox, __fmul_rn(dx, l0)), __fadd_rn(oy, __fmul_rn(dy, l0)),
-                                       __fadd_rn(oz, __fmul_rn(dz, l0)), table, net.meta, net.n_active, s_net, nullptr);
+                sdf = sdf_point<false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
+                                       __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, net.meta, net.n_active, s_net, nullptr);
             float sdf_next = __shfl_down_sync(0xffffffffu, sdf, 1);
             float alpha = neus_alpha(sdf, sdf_next, inv_s);
             int nvis = f;
@@ -128,25 +99,18 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
         if (ray_done) break;
         if (f == 31) {  // all 31 candidates were visible samples: continue contiguously
             t0 = __shfl_sync(0xffffffffu, l1, 30);
-            t1 = __fadd_rn(t0, calc_dt_(t0, 0.f, step));
+            t1 = __fadd_rn(t0, march_dt(t0, 0.f, step));
             t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
             continue;
         }
         float s_mid = __shfl_sync(0xffffffffu, lm, f);
         if (!(__shfl_sync(0xffffffffu, (int)in_range, f) != 0)) break;
         float sx = __shfl_sync(0xffffffffu, px, f), sy = __shfl_sync(0xffffffffu, py, f), sz = __shfl_sync(0xffffffffu, pz, f);
-        float tx = axis_dist_(sx, dx, ix, rmin[0], rmax[0], res.x);
-        float ty = axis_dist_(sy, dy, iy, rmin[1], rmax[1], res.y);
-        float tz = axis_dist_(sz, dz, iz, rmin[2], rmax[2], res.z);
-        float t_target = fminf(__fadd_rn(s_mid, fmaxf(fminf(fminf(tx, ty), tz), 0.0f)), far);
-        float t = s_mid;
-        do {
-            t = __fadd_rn(t, step);
-        } while (t < t_target);
-        t_mid = t;
-        float dt = calc_dt_(t_mid, 0.f, step);
+        t_mid = march_skip(rc, s_mid, step, sx, sy, sz, d, inv_d, far);
+        float dt = march_dt(t_mid, 0.f, step);
         t0 = __fmaf_rn(dt, -0.5f, t_mid);
         t1 = __fmaf_rn(dt, 0.5f, t_mid);
+        chain_open = false;
     }
     if (lane == 0) {
         sm.counts[ray] = j;

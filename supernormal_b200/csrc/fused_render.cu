@@ -53,21 +53,46 @@ __device__ __forceinline__ float dist3(float ax, float ay, float az, float bx, f
     return sqrtf(x * x + y * y + z * z);
 }
 
-// All 32 lanes must call this (shuffles); `valid` lanes get meaningful values.
-__device__ __forceinline__ SampleVals sample_vals(const LaneGeom &lg, bool valid, int s, int S, const snb_samples &sm,
-                                                  const float *__restrict__ sdf, const float *vinv, float inv_s, int lane) {
-    SampleVals v;
-    float t0 = 0.f, t1 = 1.f;
-    v.s0 = v.s1 = 0.f;
-    if (valid) {
-        t0 = __ldg(sm.t0 + s);
-        t1 = __ldg(sm.t1 + s);
-        v.s0 = __ldg(sdf + (int64_t)s * SNB_PATCH + lg.k);
-        int slot = __ldg(sm.end_slot + s);
-        // models/renderer.py:164-169: end value = next interval's start unless the intervals are not contiguous
-        v.s1 = slot >= 0 ? __ldg(sdf + ((int64_t)S + slot) * SNB_PATCH + lg.k)
-                         : (s + 1 < S ? __ldg(sdf + (int64_t)(s + 1) * SNB_PATCH + lg.k) : v.s0);
+// Raw per-(sample, ray) inputs, software-pipelined one chunk ahead so their latency overlaps the arithmetic.
+struct RawChunk {
+    float t0, t1, s0, s_end;  // s_end: SDF of the interval's own end query (only meaningful when slot >= 0)
+    int slot;
+    bool valid;
+};
+
+__device__ __forceinline__ RawChunk load_chunk(const LaneGeom &lg, int base, int n, int j0, int S, const snb_samples &sm,
+                                               const float *__restrict__ sdf) {
+    RawChunk c;
+    int j = j0 + lg.jj;
+    c.valid = lg.active && j < n;
+    c.t0 = 0.f; c.t1 = 1.f; c.s0 = 0.f; c.s_end = 0.f; c.slot = -1;
+    if (c.valid) {
+        int s = base + j;
+        c.t0 = __ldg(sm.t0 + s);
+        c.t1 = __ldg(sm.t1 + s);
+        c.s0 = __ldg(sdf + (int64_t)s * SNB_PATCH + lg.k);
+        c.slot = __ldg(sm.end_slot + s);
+        if (c.slot >= 0) c.s_end = __ldg(sdf + ((int64_t)S + c.slot) * SNB_PATCH + lg.k);
+        else if (j == n - 1) c.s_end = (s + 1 < S) ? __ldg(sdf + (int64_t)(s + 1) * SNB_PATCH + lg.k) : c.s0;  // overflow fallback only
     }
+    return c;
+}
+
+// models/renderer.py:164-169: the SDF at an interval's end is the next interval's start value unless the two are not
+// contiguous.  The next sample of the same ray sits 9 lanes up (same chunk) or in lane k of the next chunk.
+__device__ __forceinline__ float end_sdf(const LaneGeom &lg, const RawChunk &cur, const RawChunk &nxt, int j, int n, int lane) {
+    float up = __shfl_sync(kFull, cur.s0, (lane + 9) & 31);
+    float nx = __shfl_sync(kFull, nxt.s0, lg.k);
+    float contiguous = lg.jj < 2 ? up : nx;
+    return (cur.slot >= 0 || j == n - 1) ? cur.s_end : contiguous;
+}
+
+// All 32 lanes must call this (shuffles); `valid` lanes get meaningful values.
+__device__ __forceinline__ SampleVals sample_vals(const LaneGeom &lg, bool valid, float t0, float t1, float s0, float s1,
+                                                  const float *vinv, float inv_s, int lane) {
+    SampleVals v;
+    v.s0 = s0;
+    v.s1 = s1;
     float t0k = __fdiv_rn(__fmul_rn(t0, lg.num), lg.den), t1k = __fdiv_rn(__fmul_rn(t1, lg.num), lg.den);
     float px = __fadd_rn(lg.o[0], __fmul_rn(lg.d[0], t0k));
     float py = __fadd_rn(lg.o[1], __fmul_rn(lg.d[1], t0k));
@@ -128,11 +153,15 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(snb_patch_batch b, cons
     for (int a = 0; a < 9; ++a) vinv[a] = __ldg(b.v_inv + ((int64_t)patch * SNB_PATCH + lg.k) * 9 + a);
     const int base = sm.packed_info[2 * patch], n = sm.packed_info[2 * patch + 1];
     float Tc = 1.f, cn[3] = {0.f, 0.f, 0.f}, ws = 0.f, eik = 0.f;
+    RawChunk nxt = load_chunk(lg, base, n, 0, S, sm, sdf);
     for (int j0 = 0; j0 < n; j0 += 3) {
+        RawChunk cur = nxt;
+        nxt = load_chunk(lg, base, n, j0 + 3, S, sm, sdf);
         int j = j0 + lg.jj;
-        bool valid = lg.active && j < n;
+        bool valid = cur.valid;
         int s = base + j;
-        SampleVals v = sample_vals(lg, valid, s, S, sm, sdf, vinv, inv_s, lane);
+        float s1 = end_sdf(lg, cur, nxt, j, n, lane);
+        SampleVals v = sample_vals(lg, valid, cur.t0, cur.t1, cur.s0, s1, vinv, inv_s, lane);
         float T = chain_mul(Tc, __fsub_rn(1.f, v.alpha), lg);
         float w = __fmul_rn(v.alpha, T);
         if (valid) {
@@ -219,11 +248,15 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(snb_patch_batch b, cons
     float Tc = 1.f, dinv = 0.f;
     const float eik_scale = S > 0 ? eik_w * 2.f / ((float)S * SNB_PATCH * 1.0f) : 0.f;
     const int rowbase = lane - lg.c, colbase = lane - 3 * lg.r;
+    RawChunk nxt = load_chunk(lg, base, n, 0, S, sm, sdf);
     for (int j0 = 0; j0 < n; j0 += 3) {
+        RawChunk cur = nxt;
+        nxt = load_chunk(lg, base, n, j0 + 3, S, sm, sdf);
         int j = j0 + lg.jj;
-        bool valid = lg.active && j < n;
+        bool valid = cur.valid;
         int s = base + j;
-        SampleVals v = sample_vals(lg, valid, s, S, sm, sdf, vinv, inv_s, lane);
+        float s1 = end_sdf(lg, cur, nxt, j, n, lane);
+        SampleVals v = sample_vals(lg, valid, cur.t0, cur.t1, cur.s0, s1, vinv, inv_s, lane);
         float T = chain_mul(Tc, __fsub_rn(1.f, v.alpha), lg);
         float w = __fmul_rn(v.alpha, T);
         float gw = dc3[0] * v.g[0] + dc3[1] * v.g[1] + dc3[2] * v.g[2] + dws;

@@ -75,7 +75,24 @@ __global__ void __launch_bounds__(256) sdf_fwd_patch_kernel(snb_patch_batch b, s
 // ---------------------------------------------------------------------------------------------
 constexpr int kTile = 128;     // points per CTA iteration == threads per CTA
 constexpr int kDzStride = 68;  // floats; 16B-aligned rows, conflict-free 128-bit stores per quarter-warp
-constexpr int kXStride = 36;   // x_in (<=35) + constant 1 for the bias row
+constexpr int kXStride = 36;   // constant 1 (bias row) + x_in (<=35)
+
+// dW0T accumulation of one 64-point group: thread owns h in [a4,a4+4) and the NI live columns ib, ib+4, ...
+template <int NI>
+__device__ __forceinline__ void phase_b(float (&accW)[9][4], const float *__restrict__ xg, const float *__restrict__ dg) {
+#pragma unroll 4
+    for (int pp = 0; pp < 64; ++pp) {
+        float4 d = *reinterpret_cast<const float4 *>(dg + pp * kDzStride);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            float xv = xg[pp * kXStride + 4 * i];
+            accW[i][0] = fmaf(xv, d.x, accW[i][0]);
+            accW[i][1] = fmaf(xv, d.y, accW[i][1]);
+            accW[i][2] = fmaf(xv, d.z, accW[i][2]);
+            accW[i][3] = fmaf(xv, d.w, accW[i][3]);
+        }
+    }
+}
 
 // v[64] per lane -> lane l ends with the warp sums of v[2l], v[2l+1] in v[0], v[1]
 __device__ __forceinline__ void warp_transpose_reduce64(float (&v)[kH], int lane) {
@@ -105,10 +122,12 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t M = (int64_t)SNB_PATCH * (S + E);
     const uint32_t L = net.meta.n_levels, n_active = net.n_active;
-    const int K = 3 + 2 * (int)n_active;  // live input columns; column 35 is the bias row
+    const int K = 4 + 2 * (int)n_active;  // live columns of the staged input: [1 | x y z | features of the active levels]
 
-    // phase-B ownership: group g (64 threads) reduces points [64g, 64g+64); thread owns h in [4a,4a+4), i in [9ib, 9ib+9)
-    const int grp = tid >> 6, a4 = (tid & 15) * 4, i0 = ((tid >> 4) & 3) * 9;
+    // phase-B ownership: group g (64 threads) reduces points [64g, 64g+64); thread owns h in [4a,4a+4) and the live
+    // columns ib, ib+4, ib+8, ... (interleaved so that early training, with few active levels, still spreads evenly)
+    const int grp = tid >> 6, a4 = (tid & 15) * 4, ib = (tid >> 4) & 3;
+    const int n_i = (K - ib + 3) / 4;
     float accW[9][4];
 #pragma unroll
     for (int i = 0; i < 9; ++i)
@@ -137,19 +156,17 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
         float *xrow = s_x + tid * kXStride;
         if (valid) {
             layer0<false, true>(r.px, r.py, r.pz, nullptr, net.meta, n_active, s_net, const_cast<__half2 *>(feats + p * L), dz);
-            xrow[0] = r.px; xrow[1] = r.py; xrow[2] = r.pz;
+            xrow[0] = 1.f; xrow[1] = r.px; xrow[2] = r.py; xrow[3] = r.pz;
             for (uint32_t l = 0; l < n_active; ++l) {
                 float2 f = __half22float2(feats[p * L + l]);
-                xrow[3 + 2 * l] = f.x;
-                xrow[4 + 2 * l] = f.y;
+                xrow[4 + 2 * l] = f.x;
+                xrow[5 + 2 * l] = f.y;
             }
         } else {
 #pragma unroll
             for (int h = 0; h < kH; ++h) dz[h] = 0.f;
             for (int i = 0; i < K; ++i) xrow[i] = 0.f;
         }
-        for (int i = K; i < kXStride - 1; ++i) xrow[i] = 0.f;
-        xrow[kXStride - 1] = valid ? 1.f : 0.f;
         float hact[kH];
 #pragma unroll
         for (int h = 0; h < kH; ++h) {
@@ -195,21 +212,20 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
         }
         __syncthreads();
 
-        // ---- phase B: dW0T[i][h] += sum_p x[p][i] * dz[p][h]   (i == 35: bias)
+        // ---- phase B: dW0T[col][h] += sum_p x[p][col] * dz[p][h] over the live columns (col 0: bias)
         {
-            const float *xg = s_x + (grp * 64) * kXStride + i0;
+            const float *xg = s_x + (grp * 64) * kXStride + ib;
             const float *dg = s_dz + (grp * 64) * kDzStride + a4;
-#pragma unroll 4
-            for (int pp = 0; pp < 64; ++pp) {
-                float4 d = *reinterpret_cast<const float4 *>(dg + pp * kDzStride);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    float xv = xg[pp * kXStride + i];
-                    accW[i][0] = fmaf(xv, d.x, accW[i][0]);
-                    accW[i][1] = fmaf(xv, d.y, accW[i][1]);
-                    accW[i][2] = fmaf(xv, d.z, accW[i][2]);
-                    accW[i][3] = fmaf(xv, d.w, accW[i][3]);
-                }
+            switch (n_i) {
+                case 1: phase_b<1>(accW, xg, dg); break;
+                case 2: phase_b<2>(accW, xg, dg); break;
+                case 3: phase_b<3>(accW, xg, dg); break;
+                case 4: phase_b<4>(accW, xg, dg); break;
+                case 5: phase_b<5>(accW, xg, dg); break;
+                case 6: phase_b<6>(accW, xg, dg); break;
+                case 7: phase_b<7>(accW, xg, dg); break;
+                case 8: phase_b<8>(accW, xg, dg); break;
+                default: phase_b<9>(accW, xg, dg); break;
             }
         }
         __syncthreads();
@@ -218,9 +234,9 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
     // flush: folded-layout gradients
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        int col = i0 + i;  // 0..35
-        if (col < K || col == kXStride - 1) {
-            float *dst = (col == kXStride - 1) ? net_grad + kOffB0 + a4 : net_grad + kOffW0T + col * kH + a4;
+        int col = ib + 4 * i;
+        if (col < K) {
+            float *dst = (col == 0) ? net_grad + kOffB0 + a4 : net_grad + kOffW0T + (col - 1) * kH + a4;
 #pragma unroll
             for (int h = 0; h < 4; ++h) atomicAdd(dst + h, accW[i][h]);
         }

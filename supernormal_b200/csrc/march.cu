@@ -9,7 +9,7 @@
 // a ballot finds the first candidate that is not an occupied in-range sample, and the occupied
 // prefix is stored with one coalesced write.  Only the empty-space skip (whose repeated
 // `t += dt` must be replayed add-by-add to stay bit-exact) is serial.
-#include "common.cuh"
+#include "march_common.cuh"
 
 namespace snb {
 
@@ -21,34 +21,6 @@ struct MarchArgs {
     float step, cone;
 };
 
-__device__ __forceinline__ float calc_dt(float t, float cone, float dt_min) {
-    // clamp(t*cone, dt_min, 1e10) == fmaxf(dt_min, fminf(t*cone, 1e10))  (helpers_math.h:1167)
-    return fmaxf(dt_min, fminf(__fmul_rn(t, cone), 1e10f));
-}
-
-__device__ __forceinline__ bool occupied_at(float x, float y, float z, const float *roi_min, const float *roi_max,
-                                            int3 res, const uint8_t *__restrict__ grid) {
-    if (x < roi_min[0] || x > roi_max[0] || y < roi_min[1] || y > roi_max[1] || z < roi_min[2] || z > roi_max[2])
-        return false;
-    float ux = __fdiv_rn(__fsub_rn(x, roi_min[0]), __fsub_rn(roi_max[0], roi_min[0]));
-    float uy = __fdiv_rn(__fsub_rn(y, roi_min[1]), __fsub_rn(roi_max[1], roi_min[1]));
-    float uz = __fdiv_rn(__fsub_rn(z, roi_min[2]), __fsub_rn(roi_max[2], roi_min[2]));
-    int ix = min(max(__float2int_rz(__fmul_rn(ux, (float)res.x)), 0), res.x - 1);
-    int iy = min(max(__float2int_rz(__fmul_rn(uy, (float)res.y)), 0), res.y - 1);
-    int iz = min(max(__float2int_rz(__fmul_rn(uz, (float)res.z)), 0), res.z - 1);
-    return __ldg(grid + ((ix * res.y + iy) * res.z + iz)) != 0;
-}
-
-__device__ __forceinline__ float axis_dist(float p, float dir, float inv_dir, float rmin, float rmax, int r) {
-    // ((floorf(_x + 0.5 + 0.5*sign(dir)) - _x) * inv_dir) / res * (roi_max-roi_min), _x = u*res
-    float rf = (float)r;
-    float ext = __fsub_rn(rmax, rmin);
-    float u = __fdiv_rn(__fsub_rn(p, rmin), ext);
-    float fl = floorf(__fmaf_rn(copysignf(1.0f, dir), 0.5f, __fmaf_rn(rf, u, 0.5f)));
-    float diff = __fmaf_rn(rf, -u, fl);
-    return __fmul_rn(__fdiv_rn(__fmul_rn(diff, inv_dir), rf), ext);
-}
-
 template <bool EMIT>
 __global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *__restrict__ packed_info,
                                                     int64_t capacity, int32_t *__restrict__ num_steps,
@@ -57,13 +29,11 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *
     const int lane = threadIdx.x & 31;
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray >= a.n_rays) return;
-
-    const float ox = __ldg(a.rays_o + 3 * ray), oy = __ldg(a.rays_o + 3 * ray + 1), oz = __ldg(a.rays_o + 3 * ray + 2);
-    const float dx = __ldg(a.rays_d + 3 * ray), dy = __ldg(a.rays_d + 3 * ray + 1), dz = __ldg(a.rays_d + 3 * ray + 2);
-    const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+    const RoiCtx rc = make_roi_ctx(a.roi, a.res);
+    const float o[3] = {__ldg(a.rays_o + 3 * ray), __ldg(a.rays_o + 3 * ray + 1), __ldg(a.rays_o + 3 * ray + 2)};
+    const float d[3] = {__ldg(a.rays_d + 3 * ray), __ldg(a.rays_d + 3 * ray + 1), __ldg(a.rays_d + 3 * ray + 2)};
+    const float inv_d[3] = {__fdiv_rn(1.0f, d[0]), __fdiv_rn(1.0f, d[1]), __fdiv_rn(1.0f, d[2])};
     const float near = __ldg(a.t_min + ray), far = __ldg(a.t_max + ray);
-    float rmin[3] = {__ldg(a.roi), __ldg(a.roi + 1), __ldg(a.roi + 2)};
-    float rmax[3] = {__ldg(a.roi + 3), __ldg(a.roi + 4), __ldg(a.roi + 5)};
     const float dt_min = a.step;
 
     int64_t base = 0;
@@ -71,26 +41,17 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *
 
     int j = 0;
     float t0 = near;
-    float t1 = __fadd_rn(t0, calc_dt(t0, a.cone, dt_min));
+    float t1 = __fadd_rn(t0, march_dt(t0, a.cone, dt_min));
     float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 
     while (t_mid < far) {  // warp-uniform state
-        // Empty space: probe only the current candidate (warp-uniform, broadcast load) and DDA-skip; the
-        // 32-wide speculation below is only worth its cost once a sample has been found.
+        // Empty space: probe only the current candidate (warp-uniform, broadcast load) and DDA-skip; the 32-wide
+        // speculation below is only worth its cost once a sample has been found.
         {
-            float cx = __fmaf_rn(t_mid, dx, ox), cy = __fmaf_rn(t_mid, dy, oy), cz = __fmaf_rn(t_mid, dz, oz);
-            if (!occupied_at(cx, cy, cz, rmin, rmax, a.res, a.grid)) {
-                float tx = axis_dist(cx, dx, ix, rmin[0], rmax[0], a.res.x);
-                float ty = axis_dist(cy, dy, iy, rmin[1], rmax[1], a.res.y);
-                float tz = axis_dist(cz, dz, iz, rmin[2], rmax[2], a.res.z);
-                float dist = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
-                float t_target = fminf(__fadd_rn(t_mid, dist), far);
-                float t = t_mid;
-                do {
-                    t = __fadd_rn(t, dt_min);
-                } while (t < t_target);
-                t_mid = t;
-                float dt = calc_dt(t_mid, a.cone, dt_min);
+            float cx = __fmaf_rn(t_mid, d[0], o[0]), cy = __fmaf_rn(t_mid, d[1], o[1]), cz = __fmaf_rn(t_mid, d[2], o[2]);
+            if (!march_occupied(rc, cx, cy, cz, a.grid)) {
+                t_mid = march_skip(rc, t_mid, dt_min, cx, cy, cz, d, inv_d, far);
+                float dt = march_dt(t_mid, a.cone, dt_min);
                 t0 = __fmaf_rn(dt, -0.5f, t_mid);
                 t1 = __fmaf_rn(dt, 0.5f, t_mid);
                 continue;
@@ -100,28 +61,27 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *
         float l0 = t0, l1 = t1;
         for (int s = 0; s < lane; ++s) {
             l0 = l1;
-            l1 = __fadd_rn(l0, calc_dt(l0, a.cone, dt_min));
+            l1 = __fadd_rn(l0, march_dt(l0, a.cone, dt_min));
         }
         float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
-        float px = __fmaf_rn(lm, dx, ox), py = __fmaf_rn(lm, dy, oy), pz = __fmaf_rn(lm, dz, oz);
+        float px = __fmaf_rn(lm, d[0], o[0]), py = __fmaf_rn(lm, d[1], o[1]), pz = __fmaf_rn(lm, d[2], o[2]);
         bool in_range = lm < far;
-        bool occ = in_range && occupied_at(px, py, pz, rmin, rmax, a.res, a.grid);
+        bool occ = in_range && march_occupied(rc, px, py, pz, a.grid);
         unsigned stop = ~__ballot_sync(0xffffffffu, occ);
         int f = stop ? (__ffs(stop) - 1) : 32;  // lanes [0,f) are emitted samples
         if (EMIT && lane < f) {
-            int64_t o = base + j + lane;
-            if (o < capacity) {
-                t_starts[o] = l0;
-                t_ends[o] = l1;
-                if (ridx64) ridx64[o] = ray;
-                if (ridx32) ridx32[o] = ray;
+            int64_t off = base + j + lane;
+            if (off < capacity) {
+                t_starts[off] = l0;
+                t_ends[off] = l1;
+                if (ridx64) ridx64[off] = ray;
+                if (ridx32) ridx32[off] = ray;
             }
         }
         j += f;
         if (f == 32) {  // continue after lane 31's sample
-            float n0 = __shfl_sync(0xffffffffu, l1, 31);
-            t0 = n0;
-            t1 = __fadd_rn(t0, calc_dt(t0, a.cone, dt_min));
+            t0 = __shfl_sync(0xffffffffu, l1, 31);
+            t1 = __fadd_rn(t0, march_dt(t0, a.cone, dt_min));
             t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
             continue;
         }
@@ -130,18 +90,8 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a, const int32_t *
         bool s_in = __shfl_sync(0xffffffffu, (int)in_range, f) != 0;
         if (!s_in) break;  // t_mid >= far (or NaN): the reference loop exits here
         float sx = __shfl_sync(0xffffffffu, px, f), sy = __shfl_sync(0xffffffffu, py, f), sz = __shfl_sync(0xffffffffu, pz, f);
-        // advance_to_next_voxel (CS/ray_marching.cu:59-75)
-        float tx = axis_dist(sx, dx, ix, rmin[0], rmax[0], a.res.x);
-        float ty = axis_dist(sy, dy, iy, rmin[1], rmax[1], a.res.y);
-        float tz = axis_dist(sz, dz, iz, rmin[2], rmax[2], a.res.z);
-        float dist = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
-        float t_target = fminf(__fadd_rn(s_mid, dist), far);
-        float t = s_mid;
-        do {
-            t = __fadd_rn(t, dt_min);
-        } while (t < t_target);
-        t_mid = t;
-        float dt = calc_dt(t_mid, a.cone, dt_min);
+        t_mid = march_skip(rc, s_mid, dt_min, sx, sy, sz, d, inv_d, far);
+        float dt = march_dt(t_mid, a.cone, dt_min);
         t0 = __fmaf_rn(dt, -0.5f, t_mid);
         t1 = __fmaf_rn(dt, 0.5f, t_mid);
     }

@@ -141,7 +141,10 @@ def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active):
     inv_s = float(odev.inv_s())
     c, n = torch.sigmoid(out["sdf_start"] * inv_s), torch.sigmoid(out["sdf_end"] * inv_s)
     raw = ((c - n + 1e-5) / (c + 1e-5)).detach().reshape(S, 9)
-    risky = (raw.abs() < 1e-6) | ((raw - 1).abs() < 1e-6)
+    # the SDF agrees to ~4e-7, so sigmoid(inv_s * sdf) agrees to ~2e-6: a clip decision can flip when the numerator
+    # (raw = num / den) is that close to the boundary
+    num, den = (c - n + 1e-5).detach().reshape(S, 9), (c + 1e-5).detach().reshape(S, 9)
+    risky = (num.abs() < 2e-5) | ((num - den).abs() < 2e-5)
     risky[1:] |= risky[:-1].clone()
     d0, d1 = tr.buf.d_sdf0[:9 * S].view(S, 9).cpu(), tr.buf.d_sdf1[:9 * S].view(S, 9).cpu()
     es = tr.buf.end_slot[:S].cpu()
@@ -284,10 +287,13 @@ def test_fused_host_step_equals_per_kernel_path(cuda):
         if it == 0:   # identical inputs and parameters: identical results (the forward has no atomics)
             assert a.buf.totals.tolist() == b.buf.totals.tolist()
             assert torch.equal(a.buf.comp, b.buf.comp) and torch.equal(a.buf.wsum, b.buf.wsum)
-        # afterwards the fp32 atomic order of the table gradient makes the two trajectories drift by rounding noise
-        assert abs(a.buf.totals[0].item() - b.buf.totals[0].item()) <= 0.01 * a.buf.totals[0].item() + 5
-        assert torch.allclose(a.buf.wsum, b.buf.wsum, atol=2e-3)
-        assert torch.allclose(a.model.flat, b.model.flat, rtol=1e-2, atol=2e-5)
+            # one Adam step moves every touched parameter by ~lr*sign(g); only entries whose gradient is rounding noise
+            # (fp32 atomic order) may disagree
+            assert ((a.model.flat - b.model.flat).abs() > 1e-6).float().mean().item() < 1e-3
+        # afterwards Adam's normalisation amplifies that noise on near-zero-gradient entries: compare behaviour, not bits
+        la, lb = a.loss_terms(), b.loss_terms()
+        assert abs(la["n_samples"] - lb["n_samples"]) <= 0.02 * la["n_samples"] + 5
+        assert abs(la["loss"] - lb["loss"]) <= 0.05 * abs(la["loss"]) + 1e-3
     assert a.model.n_active == 3
 
 
@@ -305,7 +311,9 @@ def test_fused_occupancy_update(cuda):
         assert agree > 0.985, (it, agree)
         frac = a.grid.binary.float().mean().item()
         assert 0.08 < frac < 0.25, frac
+    # ground truth from the SDF itself at the cell centres (jitter moves a sample by at most half a cell diagonal ~0.014)
     r = torch.arange(128, device=cuda).float().add(0.5).div(64).sub(1)
     gx, gy, gz = torch.meshgrid(r, r, r, indexing="ij")
-    rad = (gx ** 2 + gy ** 2 + gz ** 2).sqrt()
-    assert a.grid.binary[rad < 0.5].all() and not a.grid.binary[rad > 0.9].any()
+    a.model.prep()
+    sdf = a.model.sdf(torch.stack([gx, gy, gz], -1).reshape(-1, 3)).view(128, 128, 128)
+    assert a.grid.binary[sdf < -0.03].all() and not a.grid.binary[sdf > 0.08].any()
