@@ -144,7 +144,9 @@ def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active):
     # the SDF agrees to ~4e-7, so sigmoid(inv_s * sdf) agrees to ~2e-6: a clip decision can flip when the numerator
     # (raw = num / den) is that close to the boundary
     num, den = (c - n + 1e-5).detach().reshape(S, 9), (c + 1e-5).detach().reshape(S, 9)
-    risky = (num.abs() < 5e-6) | ((num - den).abs() < 5e-6)   # saturated sigmoids give num == 1e-5 exactly: outside the band
+    cd, nd = c.detach().reshape(S, 9), n.detach().reshape(S, 9)
+    band = (cd * (1 - cd) + nd * (1 - nd)) * inv_s * 1e-6 + 3e-7   # |d sigmoid| for |d sdf| <= 1e-6, plus fp32 rounding of c - n
+    risky = (num.abs() < band) | ((num - den).abs() < band)
     risky[1:] |= risky[:-1].clone()
     d0, d1 = tr.buf.d_sdf0[:9 * S].view(S, 9).cpu(), tr.buf.d_sdf1[:9 * S].view(S, 9).cpu()
     es = tr.buf.end_slot[:S].cpu()
