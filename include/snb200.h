@@ -222,6 +222,11 @@ int32_t snb_render_bwd(const snb_patch_batch *h_batch, const snb_net *h_net, con
                        const float *sdf, const float *comp, const float *wsum, const float *dcomp, const float *dwsum,
                        const float *dgrad, float eikonal_weight, float *d_sdf0, float *d_sdf1, float *stats,
                        snb_stream_t stream);
+/* snb_render_fwd + snb_patch_loss + snb_render_bwd in ONE launch (lane = sample, warp scans instead of serial chains).
+ * Same results up to fp32 summation order.  d_sdf0/d_sdf1 both null: forward + losses only (stats[1..3], comp, wsum). */
+int32_t snb_render_fused(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                         const float *sdf, float normal_weight, float mask_weight, float eikonal_weight, float *comp,
+                         float *wsum, float *d_sdf0, float *d_sdf1, float *stats, snb_stream_t stream);
 /* MLP backward + hash-table scatter for all points of snb_sdf_fwd_patch.
  * table_grad f32[n_entries*2] += ...;  net_grad f32[SNB_NET_FLOATS] += gradients w.r.t. the FOLDED weights */
 int32_t snb_sdf_bwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,

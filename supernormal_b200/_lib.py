@@ -86,7 +86,7 @@ def stream() -> int:
 
 LAUNCH_COUNT = 0
 # kernels launched per entry point (memsets not counted)
-KERNELS = {"snb_occgrid_binarize": 2, "snb_compact_samples": 2, "snb_max_i64": 2, "snb_train_fwd_bwd": 10,
+KERNELS = {"snb_occgrid_binarize": 2, "snb_compact_samples": 2, "snb_max_i64": 2, "snb_train_fwd_bwd": 8,
            "snb_train_optim": 2, "snb_occgrid_update_fused": 3}
 
 

@@ -352,3 +352,274 @@ extern "C" int32_t snb_render_bwd(const snb_patch_batch *b, const snb_net *net, 
     SNB_LAUNCH_CHECK("render_bwd");
     return SNB_OK;
 }
+
+// =================================================================================================
+// Single-kernel forward + loss + backward of the render stage (training path).
+//
+// render_fwd / patch_loss / render_bwd above walk a patch three samples at a time inside ONE warp: a serial
+// chain of ~n/3 iterations of dependent loads, shuffles, divisions and square roots per patch, three launches,
+// and the forward recomputed from scratch in the backward.  Here a CTA of nine warps owns a patch: warp k is
+// in-patch ray k, lane j is sample j of a 32-sample chunk.  The 3x3 neighbourhood a dfd normal needs is exchanged
+// through shared memory, the transmittance product and the backward suffix sum are warp scans along the lanes,
+// the losses (exp_runner.py:191-203) are evaluated between the two sweeps without leaving the kernel, and patches
+// that fit one chunk (the common case) keep their forward values in registers for the backward.
+// The product order of a scan differs from the serial w = a*T; T *= 1-a of CS/render_weight.cu:107-116 by
+// fp32 rounding only (the bit-exact serial kernels stay behind snb_weight_from_alpha_patch_*).
+// =================================================================================================
+namespace snb {
+
+constexpr int kRays = SNB_PATCH;        // warps per CTA
+constexpr int kChunk = 32;
+
+struct RayConst {   // per thread, uniform within warp k
+    float o[3], d[3], num, den, vinv[9];
+};
+
+struct Pt {         // forward values of one (sample, ray)
+    float s0, s1, dt, alpha, c, n, raw, T, w;
+    float dl, dr, du, dd;
+    float g[3];
+};
+
+struct RenderSmem {
+    float s0[2][kRays][kChunk];
+    float px[2][kRays][kChunk], py[2][kRays][kChunk], pz[2][kRays][kChunk];
+    float ux[kRays][kChunk], uy[kRays][kChunk];
+    float red[kRays][4];
+};
+
+__device__ __forceinline__ float warp_incl_prod(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float u = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v *= u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float u = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// phase 1 of a chunk: load this (sample, ray), build its position, publish s0 / position for the neighbours
+__device__ __forceinline__ void pt_stage(Pt &p, const RayConst &rc, RenderSmem &sh, int buf, int k, int lane, bool valid, int s, int S,
+                                         const snb_samples &sm, const float *__restrict__ sdf) {
+    float t0 = 0.f, t1 = 1.f;
+    p.s0 = p.s1 = 0.f;
+    if (valid) {
+        t0 = __ldg(sm.t0 + s);
+        t1 = __ldg(sm.t1 + s);
+        const int slot = __ldg(sm.end_slot + s);
+        // models/renderer.py:164-169: SDF at the interval end = next start unless the intervals are not contiguous
+        const float *p0 = sdf + (int64_t)s * SNB_PATCH + k;
+        const float *p1 = slot >= 0 ? sdf + ((int64_t)S + slot) * SNB_PATCH + k : ((s + 1 < S) ? p0 + SNB_PATCH : p0);
+        p.s0 = __ldg(p0);
+        p.s1 = __ldg(p1);
+    }
+    float t0k = __fdiv_rn(__fmul_rn(t0, rc.num), rc.den), t1k = __fdiv_rn(__fmul_rn(t1, rc.num), rc.den);
+    p.dt = t1k - t0k;
+    sh.s0[buf][k][lane] = p.s0;
+    sh.px[buf][k][lane] = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], t0k));
+    sh.py[buf][k][lane] = __fadd_rn(rc.o[1], __fmul_rn(rc.d[1], t0k));
+    sh.pz[buf][k][lane] = __fadd_rn(rc.o[2], __fmul_rn(rc.d[2], t0k));
+}
+
+// phase 2 (after a CTA barrier): dfd normal (models/renderer.py:187-223) and NeuS alpha (:171-179)
+__device__ __forceinline__ void pt_finish(Pt &p, const RayConst &rc, const RenderSmem &sh, int buf, int k, int lane, bool valid, float inv_s) {
+    const int r = k / 3, c = k % 3;
+    const int kl = c > 0 ? k - 1 : k, kr = c < 2 ? k + 1 : k, ku = r > 0 ? k - 3 : k, kd = r < 2 ? k + 3 : k;
+    const float x = sh.px[buf][k][lane], y = sh.py[buf][k][lane], z = sh.pz[buf][k][lane];
+    p.dl = dist3(x, y, z, sh.px[buf][kl][lane], sh.py[buf][kl][lane], sh.pz[buf][kl][lane]);
+    p.dr = dist3(sh.px[buf][kr][lane], sh.py[buf][kr][lane], sh.pz[buf][kr][lane], x, y, z);
+    p.du = dist3(x, y, z, sh.px[buf][ku][lane], sh.py[buf][ku][lane], sh.pz[buf][ku][lane]);
+    p.dd = dist3(sh.px[buf][kd][lane], sh.py[buf][kd][lane], sh.pz[buf][kd][lane], x, y, z);
+    const float sl = sh.s0[buf][kl][lane], sr = sh.s0[buf][kr][lane], su = sh.s0[buf][ku][lane], sd = sh.s0[buf][kd][lane];
+    float proj0 = (p.s1 - p.s0) / p.dt;
+    float proj1 = c == 0 ? (sr - p.s0) / p.dr : (c == 1 ? (sr - sl) / (p.dl + p.dr) : (p.s0 - sl) / p.dl);
+    float proj2 = r == 0 ? (sd - p.s0) / p.dd : (r == 1 ? (sd - su) / (p.dd + p.du) : (p.s0 - su) / p.du);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p.g[a] = valid ? rc.vinv[3 * a] * proj0 + rc.vinv[3 * a + 1] * proj1 + rc.vinv[3 * a + 2] * proj2 : 0.f;
+    p.c = sigmoidf_(p.s0 * inv_s);
+    p.n = sigmoidf_(p.s1 * inv_s);
+    p.raw = (p.c - p.n + 1e-5f) / (p.c + 1e-5f);
+    p.alpha = valid ? fminf(fmaxf(p.raw, 0.f), 1.f) : 0.f;
+}
+
+// transmittance at the lane's sample + carry update (warp scan of 1 - alpha)
+__device__ __forceinline__ void pt_weight(Pt &p, float &Tcarry, int lane) {
+    float incl = warp_incl_prod(1.f - p.alpha, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    p.T = Tcarry * (lane == 0 ? 1.f : excl);
+    Tcarry *= __shfl_sync(kFull, incl, 31);
+    p.w = p.alpha * p.T;
+}
+
+__global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batch b, const float *__restrict__ net, snb_samples sm,
+                                                                  const float *__restrict__ sdf, float normal_w, float mask_w, float eik_w,
+                                                                  float *__restrict__ comp, float *__restrict__ wsum,
+                                                                  float *__restrict__ d_sdf0, float *__restrict__ d_sdf1,
+                                                                  float *__restrict__ stats) {
+    __shared__ RenderSmem sh;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int patch = blockIdx.x;
+    const float inv_s = __ldg(net + kOffInvS);
+    const int S = sm.totals[0];
+    const int base = sm.packed_info[2 * patch], n = sm.packed_info[2 * patch + 1];
+    const int64_t rk = (int64_t)patch * SNB_PATCH + k;
+    RayConst rc;
+    {
+        const float *o = b.rays_o + 3 * (int64_t)patch, *nn = b.plane_n + 3 * (int64_t)patch;
+        const float *dk = b.rays_d + rk * 3, *dc = b.rays_d + ((int64_t)patch * SNB_PATCH + SNB_PATCH / 2) * 3;
+        float nx = __ldg(nn), ny = __ldg(nn + 1), nz = __ldg(nn + 2);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { rc.o[a] = __ldg(o + a); rc.d[a] = __ldg(dk + a); }
+        rc.num = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(dc), nx), __fmul_rn(__ldg(dc + 1), ny)), __fmul_rn(__ldg(dc + 2), nz));
+        rc.den = __fadd_rn(__fadd_rn(__fmul_rn(rc.d[0], nx), __fmul_rn(rc.d[1], ny)), __fmul_rn(rc.d[2], nz));
+#pragma unroll
+        for (int a = 0; a < 9; ++a) rc.vinv[a] = __ldg(b.v_inv + rk * 9 + a);
+    }
+    const bool single = n <= kChunk;   // forward values stay in registers for the backward
+
+    // ---------------- forward sweep ----------------
+    float Tc = 1.f, cn[3] = {0.f, 0.f, 0.f}, ws = 0.f, eik = 0.f;
+    Pt p;
+    for (int j0 = 0, buf = 0; j0 < n; j0 += kChunk, buf ^= 1) {
+        const bool valid = j0 + lane < n;
+        pt_stage(p, rc, sh, buf, k, lane, valid, base + j0 + lane, S, sm, sdf);
+        __syncthreads();
+        pt_finish(p, rc, sh, buf, k, lane, valid, inv_s);
+        pt_weight(p, Tc, lane);
+        cn[0] += p.w * p.g[0]; cn[1] += p.w * p.g[1]; cn[2] += p.w * p.g[2];
+        ws += p.w;
+        if (valid) {
+            float nrm = sqrtf(p.g[0] * p.g[0] + p.g[1] * p.g[1] + p.g[2] * p.g[2]);
+            eik += (nrm - 1.f) * (nrm - 1.f);
+        }
+    }
+    ws = warp_sum(ws);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) cn[a] = warp_sum(cn[a]);
+    eik = warp_sum(eik);
+
+    // ---------------- losses and their seeds for ray k (exp_runner.py:169-203) ----------------
+    const int n_rays = b.n_patches * SNB_PATCH;
+    const float mask_sum = stats[0];
+    const float m = mask_w > 0.f ? (__ldg(b.mask + rk) > 0.5f ? 1.f : 0.f) : 1.f;
+    float dc3[3], nsq = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float e = (cn[a] - __ldg(b.normal_gt + 3 * rk + a)) * m;
+        nsq += e * e;
+        dc3[a] = normal_w * 2.f * e * m / mask_sum;
+    }
+    const float cw = fminf(fmaxf(ws, 1e-5f), 1.f - 1e-5f);
+    const float bce = -(m * logf(cw) + (1.f - m) * logf(1.f - cw));
+    const float dws = (ws >= 1e-5f && ws <= 1.f - 1e-5f) ? mask_w * (cw - m) / (cw * (1.f - cw)) / (float)n_rays : 0.f;
+    if (lane == 0) {
+        float *co = comp + rk * 3;
+        co[0] = cn[0]; co[1] = cn[1]; co[2] = cn[2];
+        wsum[rk] = ws;
+        sh.red[k][0] = nsq; sh.red[k][1] = bce; sh.red[k][2] = eik;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < kRays; ++q) t += sh.red[q][threadIdx.x];
+        if (t != 0.f) atomicAdd(stats + 1 + threadIdx.x, t);
+    }
+    if (n == 0 || d_sdf0 == nullptr) return;
+
+    // ---------------- backward sweep ----------------
+    const int r = k / 3, c = k % 3;
+    const float eik_scale = S > 0 ? eik_w * 2.f / ((float)S * SNB_PATCH) : 0.f;
+    float Ac = dc3[0] * cn[0] + dc3[1] * cn[1] + dc3[2] * cn[2] + dws * ws;   // sum_j gw_j w_j
+    float dinv = 0.f;
+    Tc = 1.f;
+    for (int j0 = 0, buf = 0; j0 < n; j0 += kChunk, buf ^= 1) {
+        const bool valid = j0 + lane < n;
+        const int s = base + j0 + lane;
+        if (!single) {
+            pt_stage(p, rc, sh, buf, k, lane, valid, s, S, sm, sdf);
+            __syncthreads();
+            pt_finish(p, rc, sh, buf, k, lane, valid, inv_s);
+            pt_weight(p, Tc, lane);
+        }
+        float gw = dc3[0] * p.g[0] + dc3[1] * p.g[1] + dc3[2] * p.g[2] + dws;
+        float term = valid ? gw * p.w : 0.f;
+        float pin = warp_incl_sum(term, lane);
+        float A = Ac - (pin - term);                         // sum over samples >= j of gw*w  (CS/render_weight.cu:323-338)
+        Ac -= __shfl_sync(kFull, pin, 31);
+        float dalpha = (gw * p.T - A) / fmaxf(1.f - p.alpha, 1e-10f);
+        float nrm = sqrtf(p.g[0] * p.g[0] + p.g[1] * p.g[1] + p.g[2] * p.g[2]);
+        float ek = nrm > 0.f ? eik_scale * (nrm - 1.f) / nrm : 0.f;
+        float dg[3], q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dg[a] = p.w * dc3[a] + ek * p.g[a];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) q[a] = rc.vinv[a] * dg[0] + rc.vinv[3 + a] * dg[1] + rc.vinv[6 + a] * dg[2];  // V^T dg
+        float ds0 = 0.f, ds1 = 0.f;
+        if (p.raw >= 0.f && p.raw <= 1.f) {   // clip passes the gradient on the closed interval, like torch.clamp
+            float ce = p.c + 1e-5f;
+            float dcdf = dalpha * p.n / (ce * ce), dndf = -dalpha / ce;
+            float gc = p.c * (1.f - p.c), gn = p.n * (1.f - p.n);
+            ds0 = dcdf * gc * inv_s;
+            ds1 = dndf * gn * inv_s;
+            if (valid) dinv += dcdf * gc * p.s0 + dndf * gn * p.s1;
+        }
+        float ut = q[0] / p.dt;
+        ds1 += ut;
+        ds0 -= ut;
+        float ux = q[1] / (c == 0 ? p.dr : (c == 1 ? p.dl + p.dr : p.dl));
+        float uy = q[2] / (r == 0 ? p.dd : (r == 1 ? p.dd + p.du : p.du));
+        sh.ux[k][lane] = valid ? ux : 0.f;
+        sh.uy[k][lane] = valid ? uy : 0.f;
+        __syncthreads();
+        const int rb = 3 * r;
+        float ux0 = sh.ux[rb][lane], ux1 = sh.ux[rb + 1][lane], ux2 = sh.ux[rb + 2][lane];
+        float uy0 = sh.uy[c][lane], uy1 = sh.uy[c + 3][lane], uy2 = sh.uy[c + 6][lane];
+        ds0 += c == 0 ? (-ux0 - ux1) : (c == 1 ? (ux0 - ux2) : (ux1 + ux2));
+        ds0 += r == 0 ? (-uy0 - uy1) : (r == 1 ? (uy0 - uy2) : (uy1 + uy2));
+        if (valid) {
+            d_sdf0[(int64_t)s * SNB_PATCH + k] = ds0;
+            d_sdf1[(int64_t)s * SNB_PATCH + k] = ds1;
+        }
+        if (!single) __syncthreads();   // ux/uy are rewritten by the next chunk
+    }
+    dinv = warp_sum(dinv);
+    if (lane == 0) sh.red[k][3] = dinv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < kRays; ++q) t += sh.red[q][3];
+        if (t != 0.f) atomicAdd(stats + 4, t);
+    }
+}
+
+}  // namespace snb
+
+/* forward + losses + backward of the render stage in one launch (same results as snb_render_fwd -> snb_patch_loss ->
+ * snb_render_bwd up to fp32 summation order).  d_sdf0/d_sdf1 null: forward + losses only. */
+extern "C" int32_t snb_render_fused(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const float *sdf,
+                                    float normal_weight, float mask_weight, float eikonal_weight, float *comp, float *wsum,
+                                    float *d_sdf0, float *d_sdf1, float *stats, snb_stream_t stream) {
+    int32_t rc = check_render(b, net, sm, "render_fused");
+    if (rc) return rc;
+    if (b->n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(sdf && comp && wsum && stats && b->normal_gt && b->mask, SNB_ERR_NULL, "render_fused: null buffer");
+    SNB_REQUIRE((d_sdf0 == nullptr) == (d_sdf1 == nullptr), SNB_ERR_NULL, "render_fused: d_sdf0/d_sdf1 must both be given or both be null");
+    render_fused_kernel<<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
+                                                                              eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
+    SNB_LAUNCH_CHECK("render_fused");
+    return SNB_OK;
+}

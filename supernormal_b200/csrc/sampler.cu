@@ -176,10 +176,8 @@ extern "C" int32_t snb_train_fwd_bwd(const snb_train_ctx *c, float step_size, fl
                                 &c->samples, stream))) return rc;
     if ((rc = snb_compact_samples(n, &c->samples, stream))) return rc;
     if ((rc = snb_sdf_fwd_patch(&c->batch, &c->net, &c->samples, c->sdf, c->feats, stream))) return rc;
-    if ((rc = snb_render_fwd(&c->batch, &c->net, &c->samples, c->sdf, c->comp, c->wsum, nullptr, nullptr, c->stats, stream))) return rc;
-    if ((rc = snb_patch_loss(&c->batch, c->comp, c->wsum, normal_weight, mask_weight, c->stats, c->dcomp, c->dwsum, stream))) return rc;
-    if ((rc = snb_render_bwd(&c->batch, &c->net, &c->samples, c->sdf, c->comp, c->wsum, c->dcomp, c->dwsum, nullptr, eikonal_weight, c->d_sdf0,
-                             c->d_sdf1, c->stats, stream))) return rc;
+    if ((rc = snb_render_fused(&c->batch, &c->net, &c->samples, c->sdf, normal_weight, mask_weight, eikonal_weight, c->comp, c->wsum, c->d_sdf0,
+                               c->d_sdf1, c->stats, stream))) return rc;
     cudaMemsetAsync(c->net_grad, 0, sizeof(float) * SNB_NET_FLOATS, S(stream));
     if ((rc = snb_sdf_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad, stream)))
         return rc;
