@@ -14,6 +14,13 @@
 
 namespace snb {
 
+// Empty space.  In the reference an unoccupied probe at t_mid jumps to the first point of the lattice
+//     t_mid (+) dt (+) dt (+) ...            ((+) = one rounded fp32 add, advance_to_next_voxel's do-while)
+// at or beyond the voxel exit, so EVERY point the serial marcher visits in an empty stretch lies on that one
+// lattice.  A warp therefore evaluates 32 consecutive lattice points at once -- lane k replays k adds, probes the
+// grid and runs the reference's own skip arithmetic as if it were visited -- and then follows the visited chain
+// 0 -> 0+J(0) -> ... with shuffles: the per-voxel dependent load + division chain of the serial marcher becomes
+// one parallel step plus a few ~30-cycle hops, and the visited points, hence the emitted samples, are bit-identical.
 __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, snb_net net, const float *__restrict__ roi,
                                                             int3 res, const uint8_t *__restrict__ grid, float step,
                                                             const float *__restrict__ jitter, float eps, snb_samples sm) {
@@ -24,6 +31,7 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
     if (ray >= b.n_patches) return;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const float inv_s = s_net[kOffInvS];
+    constexpr unsigned kAll = 0xffffffffu;
 
     const RoiCtx rc = make_roi_ctx(roi, res);
     const float o[3] = {__ldg(b.rays_o + 3 * ray), __ldg(b.rays_o + 3 * ray + 1), __ldg(b.rays_o + 3 * ray + 2)};
@@ -38,78 +46,107 @@ __global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, s
     float *sc1 = sm.scratch_t1 + (int64_t)ray * sm.scratch_stride;
 
     int j = 0, runs = 0;
-    bool chain_open = false, overflow = false;
+    bool chain_open = false, overflow = false, occ_mode = false;
     float T = 1.f;
+    // cone_angle == 0: calc_dt (CS/ray_marching.cu:9-14) is `step` for every finite t
     float t0 = near;
-    float t1 = __fadd_rn(t0, march_dt(t0, 0.f, step));
+    float t1 = __fadd_rn(t0, step);
     float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 
     while (t_mid < far) {
-        {   // empty space: warp-uniform probe + DDA skip (no speculation, no SDF work)
-            float cx = __fmaf_rn(t_mid, d[0], o[0]), cy = __fmaf_rn(t_mid, d[1], o[1]), cz = __fmaf_rn(t_mid, d[2], o[2]);
-            if (!march_occupied(rc, cx, cy, cz, grid)) {
-                t_mid = march_skip(rc, t_mid, step, cx, cy, cz, d, inv_d, far);
-                float dt = march_dt(t_mid, 0.f, step);
-                t0 = __fmaf_rn(dt, -0.5f, t_mid);
-                t1 = __fmaf_rn(dt, 0.5f, t_mid);
-                chain_open = false;
+        if (!occ_mode) {
+            // ---- speculative window over 32 lattice points of the empty-space lattice
+            float tm = t_mid;
+            for (int s = 0; s < lane; ++s) tm = __fadd_rn(tm, step);
+            const bool inr = tm < far;
+            const float px = __fmaf_rn(tm, d[0], o[0]), py = __fmaf_rn(tm, d[1], o[1]), pz = __fmaf_rn(tm, d[2], o[2]);
+            const bool occ = inr && march_occupied(rc, px, py, pz, grid);
+            int J = 1;
+            float land = tm;
+            if (inr && !occ) land = march_skip_count(rc, tm, step, px, py, pz, d, inv_d, far, J);
+            const unsigned occ_mask = __ballot_sync(kAll, occ), inr_mask = __ballot_sync(kAll, inr);
+            int cur = 0;
+            float last_land = t_mid;
+            bool done = false, found = false;
+            while (cur < 32) {
+                if (!((inr_mask >> cur) & 1u)) { done = true; break; }
+                if ((occ_mask >> cur) & 1u) { found = true; break; }
+                last_land = __shfl_sync(kAll, land, cur);
+                cur += __shfl_sync(kAll, J, cur);
+            }
+            if (done) break;
+            if (found) {
+                if (cur > 0) {   // reached by a skip: t0/t1 are re-centred on t_mid (CS/ray_marching.cu:173-174)
+                    t_mid = __shfl_sync(kAll, tm, cur);
+                    t0 = __fmaf_rn(step, -0.5f, t_mid);
+                    t1 = __fmaf_rn(step, 0.5f, t_mid);
+                    chain_open = false;
+                }
+                occ_mode = true;
                 continue;
             }
+            t_mid = last_land;
+            t0 = __fmaf_rn(step, -0.5f, t_mid);
+            t1 = __fmaf_rn(step, 0.5f, t_mid);
+            chain_open = false;
+            continue;
         }
+        // ---- occupied stretch: 31 candidate samples on the lattice t0 (+) dt (+) ...; lane 0 is known to be occupied
         float l0 = t0, l1 = t1;
         for (int s = 0; s < lane; ++s) {
             l0 = l1;
-            l1 = __fadd_rn(l0, march_dt(l0, 0.f, step));
+            l1 = __fadd_rn(l0, step);
         }
         float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
         float px = __fmaf_rn(lm, d[0], o[0]), py = __fmaf_rn(lm, d[1], o[1]), pz = __fmaf_rn(lm, d[2], o[2]);
         bool in_range = lm < far;
         bool occ = (lane < 31) && in_range && march_occupied(rc, px, py, pz, grid);
-        unsigned stop = ~__ballot_sync(0xffffffffu, occ);  // bit 31 always set: lane 31 only evaluates an end point
-        int f = __ffs(stop) - 1;                           // lanes [0,f) are samples, f <= 31
-        bool ray_done = false;
-        if (f > 0) {
-            // SDF at the start of every sample and (lane f) at the end of the last one; positions as the
-            // reference builds them: t_origins + t_dirs * t (models/renderer.py:84-86), separately rounded
-            float sdf = 0.f;
-            if (lane <= f)
-                sdf = sdf_point<false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
-                                       __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, net.meta, net.n_active, s_net, nullptr);
-            float sdf_next = __shfl_down_sync(0xffffffffu, sdf, 1);
-            float alpha = neus_alpha(sdf, sdf_next, inv_s);
-            int nvis = f;
-            for (int i = 0; i < f; ++i) {  // serial product, warp-uniform
-                float a = __shfl_sync(0xffffffffu, alpha, i);
-                if (!(T >= eps)) { nvis = i; break; }
-                T = __fmul_rn(T, __fsub_rn(1.f, a));
-            }
-            if (j + nvis > sm.scratch_stride) {
-                nvis = sm.scratch_stride - j;
-                overflow = true;
-            }
-            if (lane < nvis) {
-                sc0[j + lane] = l0;
-                sc1[j + lane] = l1;
-            }
-            if (nvis > 0 && !chain_open) ++runs;
-            j += nvis;
-            chain_open = (nvis == 31);
-            if (nvis < f || overflow) ray_done = true;
+        unsigned stop = ~__ballot_sync(kAll, occ);  // bit 31 always set: lane 31 only evaluates an end point
+        int f = __ffs(stop) - 1;                    // lanes [0,f) are samples, 1 <= f <= 31
+        // SDF at the start of every sample and (lane f) at the end of the last one; positions as the
+        // reference builds them: t_origins + t_dirs * t (models/renderer.py:84-86), separately rounded
+        float sdf = 0.f;
+        if (lane <= f)
+            sdf = sdf_point<false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
+                                   __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, net.meta, net.n_active, s_net, nullptr);
+        float sdf_next = __shfl_down_sync(kAll, sdf, 1);
+        float fac = lane < f ? __fsub_rn(1.f, neus_alpha(sdf, sdf_next, inv_s)) : 1.f;
+        // transmittance in front of every candidate: T * prod_{i<lane} (1 - alpha_i); NA/vol_rendering.py:730-748 keeps T >= eps
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            float u = __shfl_up_sync(kAll, fac, off);
+            if (lane >= off) fac *= u;
         }
+        float excl = __shfl_up_sync(kAll, fac, 1);
+        float Tb = lane == 0 ? T : T * excl;
+        unsigned invisible = __ballot_sync(kAll, lane < f && !(Tb >= eps));
+        int nvis = invisible ? __ffs(invisible) - 1 : f;
+        T = __shfl_sync(kAll, T * fac, f - 1);
+        bool ray_done = nvis < f;
+        if (j + nvis > sm.scratch_stride) {
+            nvis = sm.scratch_stride - j;
+            overflow = true;
+            ray_done = true;
+        }
+        if (lane < nvis) {
+            sc0[j + lane] = l0;
+            sc1[j + lane] = l1;
+        }
+        if (nvis > 0 && !chain_open) ++runs;
+        j += nvis;
+        chain_open = (nvis == 31);
         if (ray_done) break;
         if (f == 31) {  // all 31 candidates were visible samples: continue contiguously
-            t0 = __shfl_sync(0xffffffffu, l1, 30);
-            t1 = __fadd_rn(t0, march_dt(t0, 0.f, step));
+            t0 = __shfl_sync(kAll, l1, 30);
+            t1 = __fadd_rn(t0, step);
             t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+            float cx = __fmaf_rn(t_mid, d[0], o[0]), cy = __fmaf_rn(t_mid, d[1], o[1]), cz = __fmaf_rn(t_mid, d[2], o[2]);
+            if (t_mid < far && !march_occupied(rc, cx, cy, cz, grid)) occ_mode = false;   // lane 0 of a batch must be occupied
             continue;
         }
-        float s_mid = __shfl_sync(0xffffffffu, lm, f);
-        if (!(__shfl_sync(0xffffffffu, (int)in_range, f) != 0)) break;
-        float sx = __shfl_sync(0xffffffffu, px, f), sy = __shfl_sync(0xffffffffu, py, f), sz = __shfl_sync(0xffffffffu, pz, f);
-        t_mid = march_skip(rc, s_mid, step, sx, sy, sz, d, inv_d, far);
-        float dt = march_dt(t_mid, 0.f, step);
-        t0 = __fmaf_rn(dt, -0.5f, t_mid);
-        t1 = __fmaf_rn(dt, 0.5f, t_mid);
+        // candidate f is unoccupied (or beyond far: the loop condition ends the ray): back to the empty-space lattice
+        t_mid = __shfl_sync(kAll, lm, f);
+        occ_mode = false;
         chain_open = false;
     }
     if (lane == 0) {

@@ -81,4 +81,21 @@ __device__ __forceinline__ float march_skip(const RoiCtx &c, float t_mid, float 
     return t;
 }
 
+// same, also counting the lattice steps taken (used by the speculative empty-space windows of fused_march.cu)
+__device__ __forceinline__ float march_skip_count(const RoiCtx &c, float t_mid, float dt_min, float px, float py, float pz, const float *d,
+                                                  const float *inv_d, float far, int &steps) {
+    float tx = march_axis_dist(c, 0, px, d[0], inv_d[0]);
+    float ty = march_axis_dist(c, 1, py, d[1], inv_d[1]);
+    float tz = march_axis_dist(c, 2, pz, d[2], inv_d[2]);
+    float t_target = fminf(__fadd_rn(t_mid, fmaxf(fminf(fminf(tx, ty), tz), 0.0f)), far);
+    float t = t_mid;
+    int n = 0;
+    do {
+        t = __fadd_rn(t, dt_min);
+        ++n;
+    } while (t < t_target);
+    steps = n;
+    return t;
+}
+
 }  // namespace snb

