@@ -4,6 +4,9 @@
 
 namespace snb {
 
+int32_t adam_launch(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *param_f16, int64_t f16_start, float lr,
+                    float beta1, float beta2, float eps, int32_t step_count, float grad_scale, snb_stream_t stream);
+
 // Philox4x32-10 (Salmon et al. 2011), counter-based: ctr = (step lo, step hi, index, stream), key = seed
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -187,12 +190,9 @@ extern "C" int32_t snb_train_fwd_bwd(const snb_train_ctx *c, float step_size, fl
 extern "C" int32_t snb_train_optim(const snb_train_ctx *c, float lr, int32_t step_count, float grad_scale, snb_stream_t stream) {
     SNB_REQUIRE(c, SNB_ERR_NULL, "train_optim: null ctx");
     SNB_REQUIRE(c->flat_param && c->flat_grad && c->exp_avg && c->exp_avg_sq, SNB_ERR_NULL, "train_optim: null buffer");
-    int32_t rc = snb_adam_step(c->small_pad, c->flat_param, c->flat_grad, c->exp_avg, c->exp_avg_sq, nullptr, lr, 0.9f, 0.999f, 1e-8f, step_count,
-                               grad_scale, stream);
-    if (rc) return rc;
-    // levels >= n_active have exactly zero gradient and Adam state: skipping them is exact (no weight decay)
+    // one sweep over [MLP block | live levels of the table]; levels >= n_active have exactly zero gradient and Adam
+    // state, so skipping them is exact (no weight decay)
     const int64_t n_live = 2 * (int64_t)c->net.meta.offsets[c->net.n_active];
-    const int64_t o = c->small_pad;
-    return snb_adam_step(n_live, c->flat_param + o, c->flat_grad + o, c->exp_avg + o, c->exp_avg_sq + o, const_cast<void *>(c->net.table_f16), lr,
-                         0.9f, 0.999f, 1e-8f, step_count, grad_scale, stream);
+    return adam_launch(c->small_pad + n_live, c->flat_param, c->flat_grad, c->exp_avg, c->exp_avg_sq, const_cast<void *>(c->net.table_f16),
+                       c->small_pad, lr, 0.9f, 0.999f, 1e-8f, step_count, grad_scale, stream);
 }

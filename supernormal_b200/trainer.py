@@ -234,6 +234,7 @@ class FusedTrainer:
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
         self.seed = seed + 7919 * rank
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
+        self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
         self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
         dv = self.device
         n, Pn = self.n_patches, P
@@ -326,11 +327,15 @@ class FusedTrainer:
         call("snb_march_visible", rb, rn, ptr(self.grid.roi_aabb), *res, ptr(grid_u8), float(step_size), ptr(jitter), 1e-8, rs)
         call("snb_compact_samples", self.n_patches, rs)
         call("snb_sdf_fwd_patch", rb, rn, rs, ptr(b.sdf), ptr(b.feats))
-        call("snb_render_fwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), None, None, ptr(b.stats))
-        call("snb_patch_loss", rb, ptr(b.comp), ptr(b.wsum), float(c["normal_weight"]), float(c["mask_weight"]), ptr(b.stats),
-             ptr(b.dcomp), ptr(b.dwsum))
-        call("snb_render_bwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), ptr(b.dcomp), ptr(b.dwsum), None,
-             float(c["eikonal_weight"]), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
+        if self.legacy_render:   # the three serial-chain kernels the single-launch render stage replaced (kept for cross-checks)
+            call("snb_render_fwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), None, None, ptr(b.stats))
+            call("snb_patch_loss", rb, ptr(b.comp), ptr(b.wsum), float(c["normal_weight"]), float(c["mask_weight"]), ptr(b.stats),
+                 ptr(b.dcomp), ptr(b.dwsum))
+            call("snb_render_bwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), ptr(b.dcomp), ptr(b.dwsum), None,
+                 float(c["eikonal_weight"]), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
+        else:
+            call("snb_render_fused", rb, rn, rs, ptr(b.sdf), float(c["normal_weight"]), float(c["mask_weight"]), float(c["eikonal_weight"]),
+                 ptr(b.comp), ptr(b.wsum), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
         m.net_grad.zero_()
         call("snb_sdf_bwd_patch", rb, rn, rs, ptr(b.feats), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
         call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(b.stats), ptr(m.grad))
@@ -344,16 +349,8 @@ class FusedTrainer:
             dist.all_reduce(m.grad[:n_live])
             gscale = 1.0 / self.world_size
         t = self.iter_step + 1
-        if self.fused_host:
-            ctx = self._ctx(self.last_batch, None)
-            call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)
-            return
-        call("snb_adam_step", SMALL_PAD, ptr(m.flat), ptr(m.grad), ptr(m.exp_avg), ptr(m.exp_avg_sq), None,
-             self.lr, 0.9, 0.999, 1e-8, t, gscale)
-        nt = n_live - SMALL_PAD
-        if nt > 0:
-            call("snb_adam_step", nt, ptr(m.flat[SMALL_PAD:]), ptr(m.grad[SMALL_PAD:]), ptr(m.exp_avg[SMALL_PAD:]),
-                 ptr(m.exp_avg_sq[SMALL_PAD:]), ptr(m.table_f16), self.lr, 0.9, 0.999, 1e-8, t, gscale)
+        ctx = self._ctx(self.last_batch, None)
+        call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)   # one Adam sweep: MLP block + live table levels + fp16 refresh
 
     def train_step(self, batch: Optional[dict] = None, jitter: Optional[torch.Tensor] = None):
         c, rm = self.conf, self.conf["ray_marching"]
@@ -395,12 +392,12 @@ class FusedTrainer:
             return M * (4 + 4 * na) + S * 12
         if name == "snb_sdf_bwd_patch":      # read features + seeds; table-gradient read-modify-write 8 corners x 8 B per level
             return M * (4 * na + 4) + 2 * P * S * 4 + M * na * 8 * 8 * 2
-        if name == "snb_adam_step":          # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
-            return (2 * m.offsets[na]) * (16 + 16 + 2)
+        if name == "snb_train_optim":         # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
+            return (SMALL_PAD + 2 * m.offsets[na]) * (16 + 16) + 2 * m.offsets[na] * 2
         if name == "snb_march_visible":      # 40 B in per ray + 8 B per emitted sample (scratch)
             return self.n_patches * 40 + S * 8
-        if name in ("snb_render_fwd", "snb_render_bwd"):
-            return P * S * (8 + (8 if name.endswith("bwd") else 0)) + S * 12 + self.n_patches * P * (36 + 12 + 12 + 4 + 16)
+        if name == "snb_render_fused":       # sdf read + d_sdf0/d_sdf1 written per point, packed samples, per-ray constants and outputs
+            return P * S * 16 + P * E * 4 + S * 12 + self.n_patches * P * (36 + 12 + 12 + 4 + 16)
         return None
 
     def profile_kernels(self, steps: int = 20) -> dict:
@@ -433,8 +430,6 @@ class FusedTrainer:
             if nb:
                 us = sum(agg[name]) / len(agg[name])
                 calls = len(agg[name]) / steps
-                if name == "snb_adam_step":  # two launches per step (small + table): attribute to the table sweep
-                    us = max(agg[name])
                 out["dominant"] = {"name": name, "us": us, "bytes": nb, "gbs": nb / (us * 1e-6) / 1e9, "share": per_step[name] / total,
                                    "launches_per_step": calls}
                 break
