@@ -302,6 +302,26 @@ int32_t snb_train_fwd_bwd(const snb_train_ctx *h_ctx, float step_size, float ear
 /* Adam over the MLP/variance parameters and the active levels of the table (exp_runner.py:207) */
 int32_t snb_train_optim(const snb_train_ctx *h_ctx, float lr, int32_t step_count, float grad_scale, snb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Mesh extraction.  Replaces extract_fields / extract_geometry (models/renderer.py:9-34): the 64^3-chunked SDF query
+ * with a host round trip per chunk, and PyMCubes' CPU mcubes.marching_cubes (create_env.sh:14, models/renderer.py:29).
+ * A slab is the lattice planes [x0, x0+nx) x ny x nz of the res^3 grid; its last plane is the halo shared with the
+ * next slab.  Vertex numbering: [y/z-edge vertices of planes 0..nx-2 | x-edge vertices | y/z-edge vertices of plane
+ * nx-1], lattice order; vertices are in lattice-index coordinates (x + x_offset), the caller applies
+ * v/(res-1)*(max-min)+min (models/renderer.py:33).  Winding: normals point from u > iso to u <= iso.
+ * ------------------------------------------------------------------------------------- */
+/* out[i,j,k] = f(sdf(xs[i], ys[j], zs[k]));  mode as in snb_sdf_eval (2: -sdf, what extract_geometry queries) */
+int32_t snb_sdf_grid_query(const float *xs, int32_t nx, const float *ys, int32_t ny, const float *zs, int32_t nz,
+                           const snb_net *h_net, int32_t mode, float *out, snb_stream_t stream);
+/* host-only: bytes of device workspace snb_mc_count / snb_mc_emit need for an nx*ny*nz slab (0 if any dim < 2) */
+int64_t snb_mc_workspace_bytes(int32_t nx, int32_t ny, int32_t nz);
+/* classify + scans.  The first 32 bytes of the workspace then hold int64 {n_vertices, n_main, n_triangles, 0}
+ * (n_main = vertices numbered before the last plane's block).  workspace: 256-byte aligned. */
+int32_t snb_mc_count(const float *u, int32_t nx, int32_t ny, int32_t nz, float iso, void *workspace, snb_stream_t stream);
+/* vertices f32[v_cap,3], triangles i32[t_cap,3] (ids local to the slab); entries beyond the capacities are dropped */
+int32_t snb_mc_emit(const float *u, int32_t nx, int32_t ny, int32_t nz, float iso, float x_offset, const void *workspace,
+                    int64_t v_cap, int64_t t_cap, float *vertices, int32_t *triangles, snb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,13 +52,12 @@ def marching_cubes(u: np.ndarray, iso: float = 0.0, x_offset: int = 0):
         v0 = u[i, j, k]
         v1 = u[i + (axis == 0), j + (axis == 1), k + (axis == 2)]
         mu = ((iso - v0) / (v1 - v0)).astype(np.float32)
-        p = np.stack([i, j, k], -1).astype(np.float32)
+        p = np.stack([i + x_offset, j, k], -1).astype(np.float32)   # global lattice index first: slab-invariant rounding
         p[:, axis] = p[:, axis] + mu
         verts[ids[mask]] = p
     emit(cy, offA, 1)
     emit(cz, offA + cy, 2)
     emit(cx, offB, 0)
-    verts[:, 0] += np.float32(x_offset)
 
     # cells
     ins = inside.astype(np.int64)

@@ -34,7 +34,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[object, List[object]]]:
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     protos = {}
-    for ret, name, args in re.findall(r"\b(const char \*|int32_t|uint32_t)\s*(snb_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for ret, name, args in re.findall(r"\b(const char \*|int32_t|uint32_t|int64_t)\s*(snb_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         argtypes = []
         for a in [s.strip() for s in args.split(",")]:
             if a in ("void", ""):

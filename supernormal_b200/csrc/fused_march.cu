@@ -21,7 +21,7 @@ namespace snb {
 // grid and runs the reference's own skip arithmetic as if it were visited -- and then follows the visited chain
 // 0 -> 0+J(0) -> ... with shuffles: the per-voxel dependent load + division chain of the serial marcher becomes
 // one parallel step plus a few ~30-cycle hops, and the visited points, hence the emitted samples, are bit-identical.
-__global__ void __launch_bounds__(128) march_visible_kernel(snb_patch_batch b, snb_net net, const float *__restrict__ roi,
+__global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b, snb_net net, const float *__restrict__ roi,
                                                             int3 res, const uint8_t *__restrict__ grid, float step,
                                                             const float *__restrict__ jitter, float eps, snb_samples sm) {
     __shared__ __align__(16) float s_net[kNetFloats];

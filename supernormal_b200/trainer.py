@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, dp
 from ._lib import HashGridMeta, call, ptr
 
 H = 64
@@ -232,7 +232,7 @@ class FusedTrainer:
         self.buf = SampleBuffers(self.n_patches, samples_per_ray_cap, stride, self.model.n_levels, self.device)
         from .nerfacc_api import OccupancyGrid
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
-        self.seed = seed + 7919 * rank
+        self.seed = dp.rank_seed(seed, rank)   # every rank draws its own patches (weak scaling)
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
         self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
         self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
@@ -342,12 +342,8 @@ class FusedTrainer:
 
     def optimizer_step(self):
         m = self.model
-        n_live = SMALL_PAD + 2 * m.offsets[m.n_active]  # zero-gradient levels are exact no-ops for Adam without weight decay
-        gscale = 1.0
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(m.grad[:n_live])
-            gscale = 1.0 / self.world_size
+        n_live = dp.live_numel(SMALL_PAD, m.offsets, m.n_active)  # zero-gradient levels are exact no-ops for Adam without weight decay
+        gscale = dp.allreduce_live_gradients(m.grad, n_live, self.world_size)
         t = self.iter_step + 1
         ctx = self._ctx(self.last_batch, None)
         call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)   # one Adam sweep: MLP block + live table levels + fp16 refresh
