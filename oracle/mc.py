@@ -108,7 +108,7 @@ def extract_fields(bound_min, bound_max, resolution, query_func):
 def rescale(vertices, bound_min, bound_max, resolution):
     """models/renderer.py:33."""
     bmin, bmax = np.asarray(bound_min, np.float64), np.asarray(bound_max, np.float64)
-    return vertices / (resolution - 1.0) * (bmax - bmin)[None, :] + bmin[None, :]
+    return vertices.astype(np.float64) / (resolution - 1.0) * (bmax - bmin)[None, :] + bmin[None, :]   # mcubes returns float64 vertices
 
 
 def mesh_checks(vertices, triangles):

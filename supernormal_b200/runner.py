@@ -1,0 +1,134 @@
+"""Thin harness around the hot path: the eval renderer of
+exp_runner.py:397-481 (validate_normal_patch_based) and :526-577 (eval_mae), and the time-to-mesh driver
+(Runner.train + extract_geometry, exp_runner.py:147-246,483-506).  Host logic only; all tensor math is in libsnb200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import mesh
+from ._lib import call, ptr
+from .trainer import FusedTrainer, P, make_batch_struct
+
+
+@torch.no_grad()
+def render_patches(tr: FusedTrainer, batch: dict, step_size: float, jitter: Optional[torch.Tensor] = None):
+    """renderer.render(..., mode='eval') (models/renderer.py:63-276 without backward): comp_normal [N,3,3,3],
+    weight_sum [N,3,3,1] for N <= tr.n_patches patches."""
+    m, b = tr.model, tr.buf
+    n = batch["rays_d"].shape[0]
+    assert n <= tr.n_patches, "eval batch exceeds the trainer's buffer capacity"
+    zeros = lambda *s: torch.zeros(*s, device=tr.device)
+    bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"], batch["v_inv"],
+                           batch.get("normal_gt", zeros(n, P, 3)), batch.get("mask", zeros(n, P)))
+    keep = [bs]
+    m.prep(batch.get("mask", zeros(n, P)), b.stats)
+    net = m.net_struct()
+    rb, rn, rs = C.byref(bs), C.byref(net), C.byref(b.struct)
+    g = tr.grid
+    call("snb_march_visible", rb, rn, ptr(g.roi_aabb), *g._res, ptr(g.binary.view(torch.uint8)), float(step_size), ptr(jitter), 1e-8, rs)
+    call("snb_compact_samples", n, rs)
+    call("snb_sdf_fwd_patch", rb, rn, rs, ptr(b.sdf), ptr(b.feats))
+    call("snb_render_fused", rb, rn, rs, ptr(b.sdf), 0.0, 0.0, 0.0, ptr(b.comp), ptr(b.wsum), None, None, ptr(b.stats))
+    del keep
+    return b.comp[:n].view(n, 3, 3, 3).clone(), b.wsum[:n].view(n, 3, 3, 1).clone()
+
+
+@torch.no_grad()
+def validate_normal_patch_based(tr: FusedTrainer, idx: int, eval_patch_size: int = 1024, stratified: bool = True) -> torch.Tensor:
+    """World-space rendered normal map [3*(H//3), 3*(W//3), 3] of view idx from non-overlapping 3x3 patches
+    (Dataset.gen_patches_at, models/dataset_loader.py:177-221; tiling loop of exp_runner.py:423-453)."""
+    ds = tr.ds
+    dev = tr.device
+    ny, nx = ds.H // 3, ds.W // 3
+    cy, cx = torch.meshgrid(torch.arange(ny, device=dev) * 3 + 1, torch.arange(nx, device=dev) * 3 + 1, indexing="ij")
+    cy, cx = cy.reshape(-1), cx.reshape(-1)
+    out = torch.zeros(ny * nx, 3, 3, 3, device=dev)
+    step = tr.step_size(tr.iter_step)
+    for s in range(0, ny * nx, eval_patch_size):
+        e = min(s + eval_patch_size, ny * nx)
+        img = torch.full((e - s,), idx, device=dev, dtype=torch.long)
+        o, d, pn, vinv, nrm, msk = ds.patches_at(img, cx[s:e], cy[s:e], 3, 3)
+        near, far = ds.near_far_from_sphere(o[:, 1, 1], d[:, 1, 1])
+        batch = dict(rays_o=o[:, 1, 1].contiguous(), rays_d=d.view(-1, P, 3), plane_n=pn, near=near.contiguous(), far=far.contiguous(),
+                     v_inv=vinv.view(-1, P, 9))
+        jit = torch.rand(e - s, device=dev) if stratified else None
+        out[s:e] = render_patches(tr, batch, step, jit)[0]
+    return out.view(ny, nx, 3, 3, 3).permute(0, 2, 1, 3, 4).reshape(ny * 3, nx * 3, 3)
+
+
+@torch.no_grad()
+def eval_mae(tr: FusedTrainer) -> Dict[str, float]:
+    """Mean angular error in degrees over masked pixels: all views / held-out views (exp_runner.py:526-577)."""
+    ds = tr.ds
+    errs, errs_test = [], []
+    for idx in range(ds.n_images):
+        nm = validate_normal_patch_based(tr, idx)
+        nm = nm / (1e-10 + nm.norm(dim=-1, keepdim=True))
+        h, w = nm.shape[:2]
+        gt, mask = ds.normals[idx, :h, :w], ds.masks[idx, :h, :w] > 0.5
+        ae = torch.rad2deg(torch.arccos((gt * nm).sum(-1).clamp(-1, 1)))[mask]
+        errs.append(ae)
+        if idx not in ds.train_images:
+            errs_test.append(ae)
+    out = {"mae_allview": float(torch.cat(errs).mean())}
+    if errs_test:
+        out["mae_testview"] = float(torch.cat(errs_test).mean())
+    return out
+
+
+def chamfer_distance_and_f1_score(ref_points: np.ndarray, eval_points: np.ndarray, f_threshold: float = 0.5):
+    """models/cd_and_fscore.py:5-29 (symmetric mean nearest-neighbour distance / 2; F-score at f_threshold)."""
+    from scipy.spatial import KDTree
+    d_e2r, _ = KDTree(ref_points).query(eval_points, k=1, p=2)
+    d_r2e, _ = KDTree(eval_points).query(ref_points, k=1, p=2)
+    cd = (np.mean(d_e2r) + np.mean(d_r2e)) / 2
+    precision, recall = np.mean(d_e2r < f_threshold), np.mean(d_r2e < f_threshold)
+    return float(cd), float(2 * precision * recall / (precision + recall))
+
+
+def time_to_mesh(dataset, conf: dict, resolution: int = 512, device="cuda", seed: int = 0, world_scale: float = 100.0,
+                 evaluate: bool = True) -> dict:
+    """Train conf['end_iter'] iterations from random init, then extract the mesh (BASELINE.json 'time-to-mesh').
+    The synthetic scene is a sphere of radius scene.radius; world_scale maps normalised units to 'mm' so that the
+    reference's 0.5 mm F-score threshold (models/cd_and_fscore.py:5) keeps its meaning (radius 0.5 -> 50 mm)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    tr = FusedTrainer(dataset, conf, device=device, seed=seed, world_size=world, rank=rank)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(int(conf["end_iter"])):
+        tr.train_step()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    res = mesh.extract_geometry(tr.model, dataset.object_bbox_min, dataset.object_bbox_max, resolution, 0.0)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    out = {"train_s": t1 - t0, "mesh_s": t2 - t1, "time_to_mesh_s": t2 - t0, "iters": int(conf["end_iter"]), "resolution": resolution,
+           "world_size": world, "loss": tr.loss_terms()}
+    if res is None:
+        return out
+    v, t = res
+    out.update(n_vertices=int(v.shape[0]), n_triangles=int(t.shape[0]))
+    if evaluate and rank == 0:
+        r = float(dataset.scene.radius)
+        rng = np.random.RandomState(0)
+        gt = rng.randn(200000, 3)
+        gt = gt / np.linalg.norm(gt, axis=1, keepdims=True) * r * world_scale
+        # area-weighted samples of the extracted mesh
+        p = v[t.astype(np.int64)] * world_scale
+        area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
+        pick = rng.choice(len(t), 200000, p=area / area.sum())
+        uvw = rng.dirichlet([1, 1, 1], 200000)
+        ev = (p[pick] * uvw[:, :, None]).sum(1)
+        cd, f = chamfer_distance_and_f1_score(gt, ev, 0.5)
+        out.update(chamfer_mm=cd, fscore=f, radius_mean=float(np.linalg.norm(v, axis=1).mean()), radius_std=float(np.linalg.norm(v, axis=1).std()))
+        out.update(eval_mae(tr))
+    out["vertices"], out["triangles"] = v, t
+    return out
