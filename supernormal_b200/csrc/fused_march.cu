@@ -21,11 +21,12 @@ namespace snb {
 // grid and runs the reference's own skip arithmetic as if it were visited -- and then follows the visited chain
 // 0 -> 0+J(0) -> ... with shuffles: the per-voxel dependent load + division chain of the serial marcher becomes
 // one parallel step plus a few ~30-cycle hops, and the visited points, hence the emitted samples, are bit-identical.
-__global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b, snb_net net, const float *__restrict__ roi,
+__global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b, snb_net net, LevelTable lt, const float *__restrict__ roi,
                                                             int3 res, const uint8_t *__restrict__ grid, float step,
                                                             const float *__restrict__ jitter, float eps, snb_samples sm) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
     const int lane = threadIdx.x & 31;
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray >= b.n_patches) return;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
         float sdf = 0.f;
         if (lane <= f)
             sdf = sdf_point<false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
-                                   __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, net.meta, net.n_active, s_net, nullptr);
+                                   __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, s_lvl, net.n_active, s_net, nullptr);
         float sdf_next = __shfl_down_sync(kAll, sdf, 1);
         float fac = lane < f ? __fsub_rn(1.f, neus_alpha(sdf, sdf_next, inv_s)) : 1.f;
         // transmittance in front of every candidate: T * prod_{i<lane} (1 - alpha_i); NA/vol_rendering.py:730-748 keeps T >= eps
@@ -263,7 +264,7 @@ extern "C" int32_t snb_march_visible(const snb_patch_batch *b, const snb_net *ne
     SNB_REQUIRE(sm->counts && sm->end_counts && sm->totals && sm->scratch_t0 && sm->scratch_t1 && sm->scratch_stride > 0, SNB_ERR_NULL, "march_visible: null scratch");
     SNB_REQUIRE(aligned(net->net, 16), SNB_ERR_ALIGN, "march_visible: net must be 16-byte aligned");
     cudaMemsetAsync(sm->totals, 0, 4 * sizeof(int32_t), S(stream));
-    march_visible_kernel<<<(unsigned)cdiv(b->n_patches, 4), 128, 0, S(stream)>>>(*b, *net, roi, make_int3(rx, ry, rz), grid, step, jitter, eps, *sm);
+    march_visible_kernel<<<(unsigned)cdiv(b->n_patches, 4), 128, 0, S(stream)>>>(*b, *net, make_level_table(net->meta), roi, make_int3(rx, ry, rz), grid, step, jitter, eps, *sm);
     SNB_LAUNCH_CHECK("march_visible");
     return SNB_OK;
 }

@@ -8,13 +8,14 @@
 
 namespace snb {
 
-__global__ void __launch_bounds__(256) sdf_eval_kernel(int64_t n, const float *__restrict__ x, snb_net net, int mode,
+__global__ void __launch_bounds__(256) sdf_eval_kernel(int64_t n, const float *__restrict__ x, snb_net net, LevelTable lt, int mode,
                                                        float *__restrict__ out) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = sdf_point<false>(__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2), table, net.meta, net.n_active, s_net, nullptr);
+        float s = sdf_point<false>(__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2), table, s_lvl, net.n_active, s_net, nullptr);
         out[i] = mode == 1 ? sigmoidf_(-s * 80.f) : (mode == 2 ? -s : s);
     }
 }
@@ -56,17 +57,18 @@ __device__ __forceinline__ PointRef decode_point(int64_t p, int S, const snb_pat
     return r;
 }
 
-__global__ void __launch_bounds__(256) sdf_fwd_patch_kernel(snb_patch_batch b, snb_net net, snb_samples sm,
+__global__ void __launch_bounds__(256) sdf_fwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
                                                             float *__restrict__ sdf, __half2 *__restrict__ feats) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t M = (int64_t)SNB_PATCH * (S + E);
     const uint32_t L = net.meta.n_levels;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < M; p += (int64_t)gridDim.x * blockDim.x) {
         PointRef r = decode_point(p, S, b, sm);
-        sdf[p] = sdf_point<true>(r.px, r.py, r.pz, table, net.meta, net.n_active, s_net, feats + p * L);
+        sdf[p] = sdf_point<true>(r.px, r.py, r.pz, table, s_lvl, net.n_active, s_net, feats + p * L);
     }
 }
 
@@ -108,7 +110,7 @@ __device__ __forceinline__ void warp_transpose_reduce64(float (&v)[kH], int lane
     }
 }
 
-__global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch b, snb_net net, snb_samples sm,
+__global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
                                                                  const __half2 *__restrict__ feats,
                                                                  const float *__restrict__ d_sdf0,
                                                                  const float *__restrict__ d_sdf1,
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
     float *s_dz = s_net + kNetFloats;         // kTile * kDzStride
     float *s_x = s_dz + kTile * kDzStride;    // kTile * kXStride
     load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
     const int tid = threadIdx.x, lane = tid & 31;
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t M = (int64_t)SNB_PATCH * (S + E);
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
         // ---- phase A: recompute layer 0, dz = dsdf * W1 * softplus'(z); stage dz and x_in in shared memory
         float *xrow = s_x + tid * kXStride;
         if (valid) {
-            layer0<false, true>(r.px, r.py, r.pz, nullptr, net.meta, n_active, s_net, const_cast<__half2 *>(feats + p * L), dz);
+            layer0<false, true>(r.px, r.py, r.pz, nullptr, s_lvl, n_active, s_net, const_cast<__half2 *>(feats + p * L), dz);
             xrow[0] = 1.f; xrow[1] = r.px; xrow[2] = r.py; xrow[3] = r.pz;
             for (uint32_t l = 0; l < n_active; ++l) {
                 float2 f = __half22float2(feats[p * L + l]);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
                     g0 = fmaf(u.x, dz[4 * q], g0); g0 = fmaf(u.y, dz[4 * q + 1], g0); g0 = fmaf(u.z, dz[4 * q + 2], g0); g0 = fmaf(u.w, dz[4 * q + 3], g0);
                     g1 = fmaf(v.x, dz[4 * q], g1); g1 = fmaf(v.y, dz[4 * q + 1], g1); g1 = fmaf(v.z, dz[4 * q + 2], g1); g1 = fmaf(v.w, dz[4 * q + 3], g1);
                 }
-                LevelCtx c = level_ctx(net.meta, l);
+                const LevelCtx c = s_lvl[l];
                 Cell cell = cell_of(c, r.px, r.py, r.pz);
                 float2 *gt = reinterpret_cast<float2 *>(table_grad) + c.offset;
 #pragma unroll
@@ -274,7 +277,7 @@ extern "C" int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *net, i
     SNB_REQUIRE(x && out, SNB_ERR_NULL, "sdf_eval: null buffer");
     int64_t blocks = cdiv(n, 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    sdf_eval_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(n, x, *net, mode, out);
+    sdf_eval_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(n, x, *net, make_level_table(net->meta), mode, out);
     SNB_LAUNCH_CHECK("sdf_eval");
     return SNB_OK;
 }
@@ -287,7 +290,7 @@ extern "C" int32_t snb_sdf_fwd_patch(const snb_patch_batch *b, const snb_net *ne
     if (rc) return rc;
     SNB_REQUIRE(sdf && feats, SNB_ERR_NULL, "sdf_fwd_patch: null output");
     // persistent grid: the point count lives on the device (sm->totals)
-    sdf_fwd_patch_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*b, *net, *sm, sdf, (__half2 *)feats);
+    sdf_fwd_patch_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, sdf, (__half2 *)feats);
     SNB_LAUNCH_CHECK("sdf_fwd_patch");
     return SNB_OK;
 }
@@ -307,7 +310,7 @@ extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *ne
         cudaFuncSetAttribute(sdf_bwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
+    sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
     SNB_LAUNCH_CHECK("sdf_bwd_patch");
     return SNB_OK;
 }

@@ -12,6 +12,7 @@ struct LevelCtx {
     float scale;
     bool hashed;     // size < res^3 (index via coherent prime hash)
     bool pow2;       // size is a power of two
+    uint32_t magic;  // floor(2^32 / size) for the multiply-high modulo of non-power-of-two levels; 0 = use %
 };
 
 __device__ __forceinline__ LevelCtx level_ctx(const snb_hashgrid_meta &m, uint32_t l) {
@@ -25,7 +26,43 @@ __device__ __forceinline__ LevelCtx level_ctx(const snb_hashgrid_meta &m, uint32
     for (int d = 0; d < 3 && stride <= c.size; ++d) stride *= c.res;
     c.hashed = c.size < stride;
     c.pow2 = (c.size & (c.size - 1)) == 0;
+    c.magic = 0;
     return c;
+}
+
+// Fused kernels receive the per-level constants as a by-value kernel parameter built on the host (constant bank:
+// uniform operands, no per-point recomputation of the stride loop, and the division behind `magic` leaves the device).
+struct LevelTable {
+    LevelCtx lv[SNB_MAX_LEVELS];
+};
+
+static inline LevelTable make_level_table(const snb_hashgrid_meta &m) {
+    LevelTable t;
+    for (uint32_t l = 0; l < SNB_MAX_LEVELS; ++l) {
+        LevelCtx c = {};
+        if (l < m.n_levels) {
+            c.offset = m.offsets[l];
+            c.size = m.offsets[l + 1] - m.offsets[l];
+            c.res = m.resolutions[l];
+            c.scale = m.scales[l];
+            uint64_t stride = 1;
+            for (int d = 0; d < 3 && stride <= c.size; ++d) stride *= c.res;
+            c.hashed = c.size < stride;
+            c.pow2 = (c.size & (c.size - 1)) == 0;
+            c.magic = (c.pow2 || c.size == 0) ? 0u : (uint32_t)(0x100000000ull / c.size);
+        }
+        t.lv[l] = c;
+    }
+    return t;
+}
+
+// idx mod size.  Dense levels are not powers of two and SuperNormal feeds x in [-1,1], so negative cells wrap through
+// uint32 and the modulo is live on most points: q' = umulhi(idx, floor(2^32/size)) is floor(idx/size) or one less.
+__device__ __forceinline__ uint32_t level_mod(const LevelCtx &c, uint32_t idx) {
+    if (c.pow2) return idx & (c.size - 1);
+    if (c.magic == 0) return idx % c.size;
+    uint32_t r = idx - __umulhi(idx, c.magic) * c.size;
+    return r >= c.size ? r - c.size : r;
 }
 
 struct Cell {
@@ -61,7 +98,7 @@ __device__ __forceinline__ uint32_t corner_index(const LevelCtx &c, const Cell &
             if (stride <= c.size) idx += pz * stride;
         }
     }
-    return c.pow2 ? (idx & (c.size - 1)) : (idx % c.size);
+    return level_mod(c, idx);
 }
 
 // trilinear weight in the reference's multiplication order ((1*a0)*a1)*a2

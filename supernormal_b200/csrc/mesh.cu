@@ -14,17 +14,18 @@
 namespace snb {
 
 __global__ void __launch_bounds__(256) sdf_grid_query_kernel(const float *__restrict__ xs, int nx, const float *__restrict__ ys, int ny,
-                                                             const float *__restrict__ zs, int nz, snb_net net, int mode,
+                                                             const float *__restrict__ zs, int nz, snb_net net, LevelTable lt, int mode,
                                                              float *__restrict__ out) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const int64_t plane = (int64_t)ny * nz, n = plane * nx;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(p / plane);
         const int64_t r = p - (int64_t)i * plane;
         const int j = (int)(r / nz), k = (int)(r - (int64_t)j * nz);
-        float s = sdf_point<false>(__ldg(xs + i), __ldg(ys + j), __ldg(zs + k), table, net.meta, net.n_active, s_net, nullptr);
+        float s = sdf_point<false>(__ldg(xs + i), __ldg(ys + j), __ldg(zs + k), table, s_lvl, net.n_active, s_net, nullptr);
         out[p] = mode == 1 ? sigmoidf_(-s * 80.f) : (mode == 2 ? -s : s);
     }
 }
@@ -273,7 +274,7 @@ extern "C" int32_t snb_sdf_grid_query(const float *xs, int32_t nx, const float *
     if (n == 0) return SNB_OK;
     SNB_REQUIRE(xs && ys && zs && out, SNB_ERR_NULL, "sdf_grid_query: null buffer");
     SNB_REQUIRE(aligned(net->net, 16), SNB_ERR_ALIGN, "sdf_grid_query: net must be 16-byte aligned");
-    sdf_grid_query_kernel<<<grid_for(n, 256, 16), 256, 0, S(stream)>>>(xs, nx, ys, ny, zs, nz, *net, mode, out);
+    sdf_grid_query_kernel<<<grid_for(n, 256, 16), 256, 0, S(stream)>>>(xs, nx, ys, ny, zs, nz, *net, make_level_table(net->meta), mode, out);
     SNB_LAUNCH_CHECK("sdf_grid_query");
     return SNB_OK;
 }

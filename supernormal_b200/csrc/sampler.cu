@@ -66,12 +66,13 @@ __global__ void __launch_bounds__(256) sample_patches_kernel(snb_dataset ds, int
 }
 
 // ---- fused occupancy update --------------------------------------------------------------------
-__global__ void __launch_bounds__(256) occgrid_update_kernel(snb_net net, int3 res, const float *__restrict__ roi, int warmup,
+__global__ void __launch_bounds__(256) occgrid_update_kernel(snb_net net, LevelTable lt, int3 res, const float *__restrict__ roi, int warmup,
                                                              float decay, uint64_t seed, uint64_t step, float *__restrict__ occs,
                                                              const float *__restrict__ occs_prev, const uint8_t *__restrict__ binary,
                                                              const unsigned long long *__restrict__ ws) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const int64_t num_cells = (int64_t)res.x * res.y * res.z;
     const int64_t n_uniform = warmup ? 0 : num_cells / 4;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) occgrid_update_kernel(snb_net net, int3 r
             float lo = __ldg(roi + d), hi = __ldg(roi + 3 + d);
             x[d] = __fmaf_rn(u, __fsub_rn(hi, lo), lo);
         }
-        float s = sdf_point<false>(x[0], x[1], x[2], table, net.meta, net.n_active, s_net, nullptr);
+        float s = sdf_point<false>(x[0], x[1], x[2], table, s_lvl, net.n_active, s_net, nullptr);
         occs[c] = fmaxf(__fmul_rn(occs_prev[c], decay), sigmoidf_(-s * 80.f));
     }
 }
@@ -156,7 +157,7 @@ extern "C" int32_t snb_occgrid_update_fused(const snb_net *net, int32_t rx, int3
     SNB_REQUIRE(aligned(workspace, 8) && aligned(net->net, 16), SNB_ERR_ALIGN, "occgrid_update_fused: misaligned workspace/net");
     const int64_t n = (int64_t)rx * ry * rz;
     cudaMemcpyAsync(occs_prev, occs, sizeof(float) * n, cudaMemcpyDeviceToDevice, S(stream));
-    occgrid_update_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*net, make_int3(rx, ry, rz), roi, warmup, ema_decay, seed, step, occs, occs_prev,
+    occgrid_update_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*net, make_level_table(net->meta), make_int3(rx, ry, rz), roi, warmup, ema_decay, seed, step, occs, occs_prev,
                                                             binary, (const unsigned long long *)workspace);
     cudaMemsetAsync(workspace, 0, 16, S(stream));
     occgrid_sum2_kernel<<<kNumSMs * 4, 256, 0, S(stream)>>>(n, occs, (double *)workspace);

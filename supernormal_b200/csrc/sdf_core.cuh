@@ -62,7 +62,7 @@ __device__ __forceinline__ void rank1_update(float (&acc)[kH], const float *__re
 // encoded features of the active levels so the backward can skip the gathers.
 template <bool SAVE_FEAT, bool LOAD_FEAT>
 __device__ __forceinline__ void layer0(float x, float y, float z, const __half2 *__restrict__ table,
-                                       const snb_hashgrid_meta &m, uint32_t n_active, const float *s_net,
+                                       const LevelCtx *s_lvl, uint32_t n_active, const float *s_net,
                                        __half2 *feat_row, float (&acc)[kH]) {
     const float4 *b0 = reinterpret_cast<const float4 *>(s_net + kOffB0);
 #pragma unroll
@@ -78,7 +78,7 @@ __device__ __forceinline__ void layer0(float x, float y, float z, const __half2 
         if (LOAD_FEAT) {
             f = feat_row[l];
         } else {
-            LevelCtx c = level_ctx(m, l);
+            const LevelCtx c = s_lvl[l];
             Cell cell = cell_of(c, x, y, z);
             f = interp_level(c, cell, table);
             if (SAVE_FEAT) feat_row[l] = f;
@@ -105,10 +105,10 @@ __device__ __forceinline__ float layer1(const float (&acc)[kH], const float *s_n
 
 template <bool SAVE_FEAT>
 __device__ __forceinline__ float sdf_point(float x, float y, float z, const __half2 *__restrict__ table,
-                                           const snb_hashgrid_meta &m, uint32_t n_active, const float *s_net,
+                                           const LevelCtx *s_lvl, uint32_t n_active, const float *s_net,
                                            __half2 *feat_row) {
     float acc[kH];
-    layer0<SAVE_FEAT, false>(x, y, z, table, m, n_active, s_net, feat_row, acc);
+    layer0<SAVE_FEAT, false>(x, y, z, table, s_lvl, n_active, s_net, feat_row, acc);
     return layer1(acc, s_net);
 }
 
