@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
         // reference builds them: t_origins + t_dirs * t (models/renderer.py:84-86), separately rounded
         float sdf = 0.f;
         if (lane <= f)
-            sdf = sdf_point<false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
+            sdf = sdf_point<false, false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
                                    __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, s_lvl, net.n_active, s_net, nullptr);
         float sdf_next = __shfl_down_sync(kAll, sdf, 1);
         float fac = lane < f ? __fsub_rn(1.f, neus_alpha(sdf, sdf_next, inv_s)) : 1.f;

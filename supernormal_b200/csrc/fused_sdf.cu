@@ -8,7 +8,7 @@
 
 namespace snb {
 
-__global__ void __launch_bounds__(256) sdf_eval_kernel(int64_t n, const float *__restrict__ x, snb_net net, LevelTable lt, int mode,
+__global__ void __launch_bounds__(256, 2) sdf_eval_kernel(int64_t n, const float *__restrict__ x, snb_net net, LevelTable lt, int mode,
                                                        float *__restrict__ out) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);
@@ -57,7 +57,7 @@ __device__ __forceinline__ PointRef decode_point(int64_t p, int S, const snb_pat
     return r;
 }
 
-__global__ void __launch_bounds__(256) sdf_fwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
+__global__ void __launch_bounds__(256, 2) sdf_fwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
                                                             float *__restrict__ sdf, __half2 *__restrict__ feats) {
     __shared__ __align__(16) float s_net[kNetFloats];
     load_net_to_smem(s_net, net.net);

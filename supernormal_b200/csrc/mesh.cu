@@ -13,7 +13,7 @@
 
 namespace snb {
 
-__global__ void __launch_bounds__(256) sdf_grid_query_kernel(const float *__restrict__ xs, int nx, const float *__restrict__ ys, int ny,
+__global__ void __launch_bounds__(256, 2) sdf_grid_query_kernel(const float *__restrict__ xs, int nx, const float *__restrict__ ys, int ny,
                                                              const float *__restrict__ zs, int nz, snb_net net, LevelTable lt, int mode,
                                                              float *__restrict__ out) {
     __shared__ __align__(16) float s_net[kNetFloats];

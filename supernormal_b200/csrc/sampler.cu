@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) sample_patches_kernel(snb_dataset ds, int
 }
 
 // ---- fused occupancy update --------------------------------------------------------------------
-__global__ void __launch_bounds__(256) occgrid_update_kernel(snb_net net, LevelTable lt, int3 res, const float *__restrict__ roi, int warmup,
+__global__ void __launch_bounds__(256, 2) occgrid_update_kernel(snb_net net, LevelTable lt, int3 res, const float *__restrict__ roi, int warmup,
                                                              float decay, uint64_t seed, uint64_t step, float *__restrict__ occs,
                                                              const float *__restrict__ occs_prev, const uint8_t *__restrict__ binary,
                                                              const unsigned long long *__restrict__ ws) {

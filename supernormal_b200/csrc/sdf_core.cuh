@@ -33,13 +33,19 @@ __device__ __forceinline__ void load_net_to_smem(float *s_net, const float *__re
 // MUFU-based: e = exp(100 z) via ex2, log(1+e) via lg2.  Absolute error of softplus <= ~1e-9 (the hidden
 // activations are O(0.1)), relative error of the derivative ~2^-21: far below the fp32 noise of the 64-term
 // dot products that consume them.
+// Saturation shortcut: for |100 z| >= 17 softplus is max(z, 0) to within log1p(e^-17)/100 = 4e-10 and its derivative is
+// 0 / 1 to within 4e-8, so when every active lane of the warp is saturated for this hidden unit (neighbouring points
+// see near-identical pre-activations) the two MUFU ops are skipped: the XU pipe (16 lanes/clk/SM) is the scarce one.
+constexpr float kSoftplusSat = 17.f;
+template <bool SAT = true>
 __device__ __forceinline__ float softplus100(float z) {
     float bz = 100.f * z;
+    if (SAT && !__any_sync(__activemask(), fabsf(bz) < kSoftplusSat)) return fmaxf(z, 0.f);
     float e = __expf(fminf(bz, 20.f));
     return bz > 20.f ? z : __logf(1.f + e) * 0.01f;
 }
 __device__ __forceinline__ void softplus100_both(float z, float &sp, float &sg) {
-    float bz = 100.f * z;
+    float bz = 100.f * z;   // (no saturation shortcut here: the backward keeps its 64 units software-pipelined, a branch per unit costs more than the MUFU ops it saves)
     float e = __expf(fminf(bz, 20.f));
     float ope = 1.f + e;
     sp = bz > 20.f ? z : __logf(ope) * 0.01f;
@@ -89,27 +95,30 @@ __device__ __forceinline__ void layer0(float x, float y, float z, const __half2 
     }
 }
 
+// SAT: softplus saturation shortcut -- pays in the throughput-bound forward kernels; the latency-bound marcher (few warps,
+// one serial chain per ray) keeps the branch-free form.
+template <bool SAT = true>
 __device__ __forceinline__ float layer1(const float (&acc)[kH], const float *s_net) {
     float s = s_net[kOffB1];
     const float4 *w1 = reinterpret_cast<const float4 *>(s_net + kOffW1);
 #pragma unroll
     for (int q = 0; q < kH / 4; ++q) {
         float4 t = w1[q];
-        s = fmaf(t.x, softplus100(acc[4 * q + 0]), s);
-        s = fmaf(t.y, softplus100(acc[4 * q + 1]), s);
-        s = fmaf(t.z, softplus100(acc[4 * q + 2]), s);
-        s = fmaf(t.w, softplus100(acc[4 * q + 3]), s);
+        s = fmaf(t.x, softplus100<SAT>(acc[4 * q + 0]), s);
+        s = fmaf(t.y, softplus100<SAT>(acc[4 * q + 1]), s);
+        s = fmaf(t.z, softplus100<SAT>(acc[4 * q + 2]), s);
+        s = fmaf(t.w, softplus100<SAT>(acc[4 * q + 3]), s);
     }
     return s;
 }
 
-template <bool SAVE_FEAT>
+template <bool SAVE_FEAT, bool SAT = true>
 __device__ __forceinline__ float sdf_point(float x, float y, float z, const __half2 *__restrict__ table,
                                            const LevelCtx *s_lvl, uint32_t n_active, const float *s_net,
                                            __half2 *feat_row) {
     float acc[kH];
     layer0<SAVE_FEAT, false>(x, y, z, table, s_lvl, n_active, s_net, feat_row, acc);
-    return layer1(acc, s_net);
+    return layer1<SAT>(acc, s_net);
 }
 
 // NeuS opacity of an interval from the SDF at its two ends (models/renderer.py:173-179)
