@@ -4,19 +4,41 @@
 //                   are built in-kernel (models/renderer.py:146-159), encode + MLP fused, features kept
 //   sdf_bwd_patch   MLP backward (recomputing layer 0 from the kept features), weight gradients as a
 //                   shared-memory-tiled contraction, hash-table scatter with vector fp32 atomics
-#include "sdf_core.cuh"
+#include "sdf_mma.cuh"
 
 namespace snb {
 
-__global__ void __launch_bounds__(256, 2) sdf_eval_kernel(int64_t n, const float *__restrict__ x, snb_net net, LevelTable lt, int mode,
-                                                       float *__restrict__ out) {
-    __shared__ __align__(16) float s_net[kNetFloats];
-    load_net_to_smem(s_net, net.net);
+constexpr int kFwdWarps = 4;   // warps per CTA of the tensor-core forward kernels
+constexpr size_t kFwdSmemBytes = sizeof(float) * kMmaSmemFloats(kFwdWarps);
+
+struct FwdSmem {
+    float *net, *whi, *wlo, *xs;
+};
+__device__ __forceinline__ FwdSmem fwd_smem_setup(float *smem, const float *g_net) {
+    FwdSmem s;
+    s.net = smem;
+    s.whi = s.net + kNetFloats;
+    s.wlo = s.whi + kWRows * kWStride;
+    s.xs = s.wlo + kWRows * kWStride + (threadIdx.x >> 5) * 32 * kXsStride;
+    load_net_to_smem(s.net, g_net);
+    stage_w_split(s.net, s.whi, s.wlo);
+    return s;
+}
+
+__global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_eval_kernel(int64_t n, const float *__restrict__ x, snb_net net, LevelTable lt, int mode,
+                                                                     float *__restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    const FwdSmem sh = fwd_smem_setup(smem, net.net);
     const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = sdf_point<false>(__ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2), table, s_lvl, net.n_active, s_net, nullptr);
-        out[i] = mode == 1 ? sigmoidf_(-s * 80.f) : (mode == 2 ? -s : s);
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (valid) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        float s = warp_sdf_mma<false, true>(valid, px, py, pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, nullptr, lane);
+        if (valid) out[i] = mode == 1 ? sigmoidf_(-s * 80.f) : (mode == 2 ? -s : s);
     }
 }
 
@@ -57,18 +79,25 @@ __device__ __forceinline__ PointRef decode_point(int64_t p, int S, const snb_pat
     return r;
 }
 
-__global__ void __launch_bounds__(256, 2) sdf_fwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
-                                                            float *__restrict__ sdf, __half2 *__restrict__ feats) {
-    __shared__ __align__(16) float s_net[kNetFloats];
-    load_net_to_smem(s_net, net.net);
+__global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_fwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
+                                                                          float *__restrict__ sdf, __half2 *__restrict__ feats) {
+    extern __shared__ __align__(16) float smem[];
+    const FwdSmem sh = fwd_smem_setup(smem, net.net);
     const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t M = (int64_t)SNB_PATCH * (S + E);
     const uint32_t L = net.meta.n_levels;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < M; p += (int64_t)gridDim.x * blockDim.x) {
-        PointRef r = decode_point(p, S, b, sm);
-        sdf[p] = sdf_point<true>(r.px, r.py, r.pz, table, s_lvl, net.n_active, s_net, feats + p * L);
+    const int lane = threadIdx.x & 31;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x; p0 < M; p0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = p0 + threadIdx.x;
+        const bool valid = p < M;
+        PointRef r;
+        r.px = r.py = r.pz = 0.f;
+        if (valid) r = decode_point(p, S, b, sm);
+        float s = warp_sdf_mma<true, true>(valid, r.px, r.py, r.pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs,
+                                           feats + (valid ? p : 0) * L, lane);
+        if (valid) sdf[p] = s;
     }
 }
 
@@ -275,9 +304,14 @@ extern "C" int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *net, i
     SNB_REQUIRE(n >= 0 && mode >= 0 && mode <= 2, SNB_ERR_ARG, "sdf_eval: bad n/mode");
     if (n == 0) return SNB_OK;
     SNB_REQUIRE(x && out, SNB_ERR_NULL, "sdf_eval: null buffer");
-    int64_t blocks = cdiv(n, 256);
+    int64_t blocks = cdiv(n, 32 * kFwdWarps);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    sdf_eval_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(n, x, *net, make_level_table(net->meta), mode, out);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sdf_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
+        configured = true;
+    }
+    sdf_eval_kernel<<<(unsigned)blocks, 32 * kFwdWarps, kFwdSmemBytes, S(stream)>>>(n, x, *net, make_level_table(net->meta), mode, out);
     SNB_LAUNCH_CHECK("sdf_eval");
     return SNB_OK;
 }
@@ -290,7 +324,12 @@ extern "C" int32_t snb_sdf_fwd_patch(const snb_patch_batch *b, const snb_net *ne
     if (rc) return rc;
     SNB_REQUIRE(sdf && feats, SNB_ERR_NULL, "sdf_fwd_patch: null output");
     // persistent grid: the point count lives on the device (sm->totals)
-    sdf_fwd_patch_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, sdf, (__half2 *)feats);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sdf_fwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmemBytes);
+        configured = true;
+    }
+    sdf_fwd_patch_kernel<<<kNumSMs * 4, 32 * kFwdWarps, kFwdSmemBytes, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, sdf, (__half2 *)feats);
     SNB_LAUNCH_CHECK("sdf_fwd_patch");
     return SNB_OK;
 }
