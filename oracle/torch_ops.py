@@ -126,13 +126,14 @@ class OccupancyGrid:
     """NA/grid.py:113-294 (AABB contraction only: contract_inv = x*(max-min)+min,
     CS/include/helpers_contraction.h:23-28)."""
 
-    def __init__(self, roi_aabb, resolution=128):
-        self.roi_aabb = torch.as_tensor(roi_aabb, dtype=torch.float32)
-        self.resolution = torch.tensor([resolution] * 3, dtype=torch.int32)
+    def __init__(self, roi_aabb, resolution=128, device="cpu"):
+        self.device = torch.device(device)
+        self.roi_aabb = torch.as_tensor(roi_aabb, dtype=torch.float32).to(self.device)
+        self.resolution = torch.tensor([resolution] * 3, dtype=torch.int32, device=self.device)
         self.num_cells = resolution ** 3
-        self.binary = torch.zeros([resolution] * 3, dtype=torch.bool)
-        self.occs = torch.zeros(self.num_cells)
-        r = torch.arange(resolution)
+        self.binary = torch.zeros([resolution] * 3, dtype=torch.bool, device=self.device)
+        self.occs = torch.zeros(self.num_cells, device=self.device)
+        r = torch.arange(resolution, device=self.device)
         self.grid_coords = torch.stack(torch.meshgrid(r, r, r, indexing="ij"), -1).reshape(-1, 3)
 
     def update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256,
@@ -140,17 +141,17 @@ class OccupancyGrid:
         """NA/grid.py:197-239. `rand` [n,3] / `indices` injectable for parity tests."""
         if indices is None:
             if step < warmup_steps:
-                indices = torch.arange(self.num_cells)
+                indices = torch.arange(self.num_cells, device=self.device)
             else:
                 N = self.num_cells // 4
-                uni = torch.randint(self.num_cells, (N,))
+                uni = torch.randint(self.num_cells, (N,), device=self.device)
                 occ_idx = torch.nonzero(self.binary.flatten())[:, 0]
                 if N < len(occ_idx):
-                    occ_idx = occ_idx[torch.randint(len(occ_idx), (N,))]
+                    occ_idx = occ_idx[torch.randint(len(occ_idx), (N,), device=self.device)]
                 indices = torch.cat([uni, occ_idx])
         coords = self.grid_coords[indices]
         if rand is None:
-            rand = torch.rand(coords.shape)
+            rand = torch.rand(coords.shape, device=self.device)
         x = (coords + rand) / self.resolution
         x = x * (self.roi_aabb[3:] - self.roi_aabb[:3]) + self.roi_aabb[:3]
         occ = occ_eval_fn(x).squeeze(-1)
@@ -311,10 +312,14 @@ def _diff_mask(t0, t1):
 class NeuSRenderer:
     """models/renderer.py:37-276 (patch-based `render`), CPU, our oracle operators."""
 
-    def __init__(self, sdf_network: SDFNetwork, deviation: SingleVariance, gradient_method="dfd"):
+    def __init__(self, sdf_network: SDFNetwork, deviation: SingleVariance, gradient_method="dfd", ops=None, device="cpu"):
+        """`ops` = namespace providing render_weight_from_alpha_patch_based / accumulate_along_rays_patch_based
+        (default: this module's CPU oracle operators; oracle/cuda_path.py plugs in a nerfacc-shaped CUDA module)."""
+        import sys
+        self.ops = ops if ops is not None else sys.modules[__name__]
         self.sdf_network, self.deviation_network = sdf_network, deviation
-        self.scene_aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0])
-        self.occupancy_grid = OccupancyGrid(self.scene_aabb, 128)
+        self.scene_aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], device=device)
+        self.occupancy_grid = OccupancyGrid(self.scene_aabb, 128, device=device)
         self.sampling_step_size = 0.01
         self.gradient_method = gradient_method
 
@@ -350,7 +355,7 @@ class NeuSRenderer:
             pidx = pidx.long()
             S = pidx.shape[0]
             if S == 0:
-                return {"comp_normal": torch.zeros(Np, pH, pW, 3), "gradients": None, "n_samples": 0}
+                return {"comp_normal": torch.zeros(Np, pH, pW, 3, device=rays_o.device), "gradients": None, "n_samples": 0}
             # plane fan-out, models/renderer.py:146-149
             num = (d_c * plane_n).sum(-1, keepdim=True)[pidx][:, None, None, :]
             den = (rays_d * plane_n[:, None, None, :]).sum(-1, keepdim=True)[pidx]
@@ -367,7 +372,7 @@ class NeuSRenderer:
         s1 = _next_start_or_own_end(s0, sdf_all[S:], dm)
         inv_s = self.deviation_network.inv_s()
         alpha = neus_alpha(s0, s1, inv_s)
-        w = render_weight_from_alpha_patch_based(alpha.reshape(S, pH * pW, 1), pidx)
+        w = self.ops.render_weight_from_alpha_patch_based(alpha.reshape(S, pH * pW, 1), pidx)
         method = gradient_method or self.gradient_method
         if method == "dfd":  # models/renderer.py:187-223
             with torch.no_grad():
@@ -386,8 +391,8 @@ class NeuSRenderer:
             grads = self.sdf_network.gradient(p0.reshape(-1, 3)).reshape(S, pH, pW, 3)
         else:
             raise ValueError(method)
-        wsum = accumulate_along_rays_patch_based(w, pidx, n_patches=Np).reshape(Np, pH, pW, 1)
-        comp = accumulate_along_rays_patch_based(w, pidx, values=grads.reshape(S, pH * pW, 3), n_patches=Np)
+        wsum = self.ops.accumulate_along_rays_patch_based(w, pidx, n_patches=Np).reshape(Np, pH, pW, 1)
+        comp = self.ops.accumulate_along_rays_patch_based(w, pidx, values=grads.reshape(S, pH * pW, 3), n_patches=Np)
         return {"s_val": 1 / inv_s, "weight_sum": wsum, "gradients": grads, "comp_normal": comp.reshape(Np, pH, pW, 3),
                 "n_samples": S, "samples": (pidx, t0c, t1c), "sdf_all": sdf_all, "diff_mask": dm, "sdf_start": s0, "sdf_end": s1, "alpha": alpha, "weights": w}
 
@@ -445,7 +450,7 @@ class Trainer:
         o, d, pn, Vi, nrm, msk = batch
         ps = c["patch_size"]
         near, far = self.ds.near_far_from_sphere(o[:, ps // 2, ps // 2], d[:, ps // 2, ps // 2])
-        out = self.renderer.render(o, d, pn, near, far, Vi, jitter=torch.rand(o.shape[0]))
+        out = self.renderer.render(o, d, pn, near, far, Vi, jitter=torch.rand(o.shape[0], device=o.device))
         if out["gradients"] is None:
             self._set_lr()
             return None, out
