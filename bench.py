@@ -102,6 +102,25 @@ def cpu_port_run(steps, warmup, n_patches=64, threads=None):
     return n_patches * 9 * steps / dt, dt / steps * 1e3, threads, f"{steps} steps of {n_patches} patches x 9 rays (of 2048) at the start of the schedule, analytic initial occupancy grid, no grid updates in the timed steps"
 
 
+def ref_cuda_path_run(dev, warmup, steps, backend="reference"):
+    """The reference-shaped step on this GPU (oracle/cuda_path.py): the UNMODIFIED reference nerfacc kernels
+    (oracle/_ref) + ATen ops + torch.optim.Adam, with the encoding behind tiny-cuda-nn's calling convention
+    (tcnn itself is not in the image).  Same workload, same schedule window [warmup, warmup+steps)."""
+    from oracle import cuda_path as cp
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    if backend == "reference" and cp.load_ref_nerfacc() is None:
+        return None
+    ds = SyntheticDataset(SyntheticScene(), device=dev)
+    tr = cp.CudaTrainer(ds, dict(DILIGENT_CONF), backend=backend, seed=0, device=dev)
+    ms, spr = cp.time_steps(tr, steps, warmup)
+    n = DILIGENT_CONF["batch_size"]
+    return {"value": n * 9 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "samples_per_ray_last": spr,
+            "what": ("unmodified reference nerfacc 0.3.5 kernels (oracle/_ref, sm_100a) + ATen/autograd/torch.optim.Adam step; "
+                     "encoding = supernormal_b200.tcnn_api under tcnn's convention (all 14 levels, mask after, fp16 recast per forward) "
+                     "because tiny-cuda-nn is absent") if backend == "reference" else
+                    "same ATen/autograd step over the drop-in modules supernormal_b200.nerfacc_api + tcnn_api (no fused trainer)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -123,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=10 ** 9, help="cap on the e2e arm's steps (default: same K)")
+    ap.add_argument("--ref-cuda-steps", type=int, default=100, help="steps of the reference-shaped CUDA path timed beside ours at N=1 (0 = skip)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -163,8 +183,12 @@ def main():
         barrier()
         torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly the timed steps
         ev0.record()
+        Kr = min(K, args.ref_cuda_steps) if world == 1 else 0
+        evr = torch.cuda.Event(enable_timing=True)
         for i in range(K):
             tr.train_step()
+            if i + 1 == Kr:
+                evr.record()   # our time over the same schedule window the reference-shaped path is timed on
         ev1.record()
         barrier()
         torch.cuda.profiler.stop()
@@ -223,6 +247,17 @@ def main():
             dk = prof["dominant"]
             line["roofline"] = {"bound": "hbm", "kernel": dk["name"], "achieved": dk["gbs"], "peak": peak, "unit": "GB/s", "frac": dk["gbs"] / peak,
                                 "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": dk["bytes"], "avg_us": dk["us"]}
+        if Kr > 0:
+            ours_ms = ev0.elapsed_time(evr) / Kr
+            for backend, key in (("reference", "reference_cuda_path"), ("dropin", "dropin_api_path")):
+                try:
+                    r = ref_cuda_path_run(dev, W, Kr, backend)
+                except Exception as e:   # measurement aid only: never take the bench line down with it
+                    r = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+                if r is not None:
+                    if "ms_per_step" in r:
+                        r["ours_ms_per_step_same_window"] = ours_ms
+                    line[key] = r
         if world == 1 and not args.no_cpu:
             v, cms, threads, sample = cpu_port_run(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": cms}
