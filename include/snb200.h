@@ -203,6 +203,10 @@ int32_t snb_march_visible(const snb_patch_batch *h_batch, const snb_net *h_net, 
 int32_t snb_compact_samples(int32_t n_patches, const snb_samples *h_samples, snb_stream_t stream);
 /* SDF at arbitrary points, no grad.  mode 0: sdf, 1: sigmoid(-80*sdf) (models/renderer.py:56-60), 2: -sdf */
 int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *h_net, int32_t mode, float *out, snb_stream_t stream);
+/* SDF and its analytic gradient d sdf / d x in ONE pass (forward-mode through encode + MLP on the tensor cores):
+ * what SDFNetwork.gradient (models/fields.py:107-119) returns for `ad` normals (models/renderer.py:225-226, :345),
+ * without the autograd double pass.  sdf: f32[n] or null; grad: f32[n,3]. */
+int32_t snb_sdf_eval_grad(int64_t n, const float *x, const snb_net *h_net, float *sdf, float *grad, snb_stream_t stream);
 /* SDF at the 9 plane-projected rays of every sample start (+ own ends), keeping the encoded features.
  * sdf: [9*(capacity+end_capacity)]: starts at s*9+k, ends at 9*S + slot*9+k.  feats: half2 [points, n_levels] */
 int32_t snb_sdf_fwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,

@@ -42,6 +42,31 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_eval_kernel(int64_t n, 
     }
 }
 
+// sdf and d sdf / d x in one pass (analytic normals, models/fields.py:107-119 without the autograd graph)
+constexpr size_t kGradSmemBytes = kFwdSmemBytes + sizeof(float) * kFwdWarps * 3 * 32 * kTsStride;
+
+__global__ void __launch_bounds__(32 * kFwdWarps, 2) sdf_eval_grad_kernel(int64_t n, const float *__restrict__ x, snb_net net, LevelTable lt,
+                                                                          float *__restrict__ sdf, float *__restrict__ grad) {
+    extern __shared__ __align__(16) float smem[];
+    const FwdSmem sh = fwd_smem_setup(smem, net.net);
+    float *ts = smem + kMmaSmemFloats(kFwdWarps) + (threadIdx.x >> 5) * 3 * 32 * kTsStride;
+    const LevelCtx *s_lvl = lt.lv;
+    const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool valid = i < n;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (valid) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
+        float g[3];
+        float s = warp_sdf_grad_mma<true>(valid, px, py, pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, ts, lane, g);
+        if (valid) {
+            if (sdf) sdf[i] = s;
+            grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2];
+        }
+    }
+}
+
 struct PointRef {
     int s, k, patch;
     bool is_end;
@@ -313,6 +338,24 @@ extern "C" int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *net, i
     }
     sdf_eval_kernel<<<(unsigned)blocks, 32 * kFwdWarps, kFwdSmemBytes, S(stream)>>>(n, x, *net, make_level_table(net->meta), mode, out);
     SNB_LAUNCH_CHECK("sdf_eval");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_sdf_eval_grad(int64_t n, const float *x, const snb_net *net, float *sdf, float *grad, snb_stream_t stream) {
+    int32_t rc = check_net(net, "sdf_eval_grad");
+    if (rc) return rc;
+    SNB_REQUIRE(n >= 0, SNB_ERR_ARG, "sdf_eval_grad: n < 0");
+    if (n == 0) return SNB_OK;
+    SNB_REQUIRE(x && grad, SNB_ERR_NULL, "sdf_eval_grad: null buffer");
+    int64_t blocks = cdiv(n, 32 * kFwdWarps);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sdf_eval_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemBytes);
+        configured = true;
+    }
+    sdf_eval_grad_kernel<<<(unsigned)blocks, 32 * kFwdWarps, kGradSmemBytes, S(stream)>>>(n, x, *net, make_level_table(net->meta), sdf, grad);
+    SNB_LAUNCH_CHECK("sdf_eval_grad");
     return SNB_OK;
 }
 

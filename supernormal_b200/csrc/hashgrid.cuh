@@ -121,4 +121,37 @@ __device__ __forceinline__ __half2 interp_level(const LevelCtx &c, const Cell &c
     return acc;
 }
 
+// value (fp16-faithful, as interp_level) and d(value)/dx of one level sharing the 8 corner loads.  The derivative is
+// tiny-cuda-nn's dy_dx for linear interpolation (encodings/grid.h, kernel_grid with dy_dx != nullptr): fp32,
+//   d/dx_d = scale * sum over the 4 corner pairs along d of  a_e0 * a_e1 * (v_right - v_left).
+__device__ __forceinline__ __half2 interp_level_grad(const LevelCtx &c, const Cell &cell, const __half2 *__restrict__ table,
+                                                     float2 (&dv)[3]) {
+    const __half2 *t = table + c.offset;
+    __half2 v[8];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) v[k] = __ldg(t + corner_index(c, cell, k));
+    __half2 acc = __float2half2_rn(0.f);
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) acc = __hfma2(__float2half2_rn(corner_weight(cell, k)), v[k], acc);
+    float2 vf[8];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) vf[k] = __half22float2(v[k]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int e0 = (d + 1) % 3, e1 = (d + 2) % 3;
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {
+            if ((k >> d) & 1u) continue;
+            const float a0 = ((k >> e0) & 1u) ? cell.w[e0] : 1.f - cell.w[e0];
+            const float a1 = ((k >> e1) & 1u) ? cell.w[e1] : 1.f - cell.w[e1];
+            const float w = a0 * a1;
+            sx = fmaf(w, vf[k | (1u << d)].x - vf[k].x, sx);
+            sy = fmaf(w, vf[k | (1u << d)].y - vf[k].y, sy);
+        }
+        dv[d] = make_float2(c.scale * sx, c.scale * sy);
+    }
+    return acc;
+}
+
 }  // namespace snb

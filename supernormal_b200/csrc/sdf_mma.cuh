@@ -165,6 +165,134 @@ __device__ __forceinline__ float warp_sdf_mma(bool valid, float x, float y, floa
     return warp_layer1<SAT>(acc, xs, s_net, lane);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SDF and its analytic gradient in ONE pass (north star item 3): forward-mode through the MLP.
+//   z = W0 [x, f(x)] + b0,  sdf = W1 softplus(z) + b1,
+//   d sdf / d x_d = sum_h W1[h] sigmoid(100 z_h) * ( W0[h][d] + sum_j W0feat[h][j] * d f_j / d x_d ).
+// The three tangent contractions [32 points x 2L] x [2L x 64] run on the tensor cores like the value one.  Tangents are
+// fp32 numbers (not fp16-exact), so they are split hi + lo in registers when the A fragments are loaded and three MMAs
+// (hi*hi, lo*hi, hi*lo) keep the products exact to 2^-22: a single TF32 pass would cost ~5e-4 relative on the normal.
+constexpr int kTsStride = 36;   // floats per point row of a tangent tile (32 feature columns; conflict-free A-fragment loads)
+
+template <bool SAT>
+__device__ __forceinline__ float warp_sdf_grad_mma(bool valid, float x, float y, float z, const __half2 *__restrict__ table,
+                                                   const LevelCtx *lvl, uint32_t n_active, const float *s_net, const float *s_whi,
+                                                   const float *s_wlo, float *xs, float *ts, int lane, float (&grad)[3]) {
+    const int ksteps = (int)(2 * n_active + 7) >> 3;
+    const int g = lane >> 2, t = lane & 3;
+    float *row = xs + lane * kXsStride;
+    __syncwarp();
+    for (uint32_t l = 0; l < n_active; ++l) {
+        float2 ff = make_float2(0.f, 0.f);
+        float2 dv[3] = {ff, ff, ff};
+        if (valid) {
+            const LevelCtx c = lvl[l];
+            Cell cell = cell_of(c, x, y, z);
+            ff = __half22float2(interp_level_grad(c, cell, table, dv));
+        }
+        *reinterpret_cast<float2 *>(row + 2 * l) = ff;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) *reinterpret_cast<float2 *>(ts + (d * 32 + lane) * kTsStride + 2 * l) = dv[d];
+    }
+    for (int cidx = 2 * (int)n_active; cidx < 8 * ksteps; ++cidx) {
+        row[cidx] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ts[(d * 32 + lane) * kTsStride + cidx] = 0.f;
+    }
+    stage_point(xs, lane, valid ? x : 0.f, valid ? y : 0.f, valid ? z : 0.f);
+    __syncwarp();
+
+    float acc[2][8][4];
+    warp_layer0_mma(acc, xs, s_net, s_whi, s_wlo, ksteps, lane);
+    // softplus / sigmoid in fragment layout: acc <- W1[h] * sigmoid(100 z_h); sdf partial sums on the side
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const float2 w1 = *reinterpret_cast<const float2 *>(s_net + kOffW1 + 8 * nt + 2 * t);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float sp, sg;
+            softplus100_both(acc[r >> 1][nt][2 * (r & 1)], sp, sg);
+            part[r] = fmaf(w1.x, sp, part[r]);
+            acc[r >> 1][nt][2 * (r & 1)] = w1.x * sg;
+            softplus100_both(acc[r >> 1][nt][2 * (r & 1) + 1], sp, sg);
+            part[r] = fmaf(w1.y, sp, part[r]);
+            acc[r >> 1][nt][2 * (r & 1) + 1] = w1.y * sg;
+        }
+    }
+    float gpart[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float tacc[2][8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float2 wd = *reinterpret_cast<const float2 *>(s_net + kOffW0T + d * kH + 8 * nt + 2 * t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                tacc[mt][nt][0] = wd.x; tacc[mt][nt][1] = wd.y; tacc[mt][nt][2] = wd.x; tacc[mt][nt][3] = wd.y;
+            }
+        }
+        const float *tile = ts + d * 32 * kTsStride;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float *r0 = tile + (16 * mt + g) * kTsStride + 8 * ks + t;
+                const float v[4] = {r0[0], r0[8 * kTsStride], r0[4], r0[8 * kTsStride + 4]};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    ahi[mt][e] = to_tf32(v[e]);
+                    alo[mt][e] = to_tf32(v[e] - __uint_as_float(ahi[mt][e]));
+                }
+            }
+            const float *wh = s_whi + (8 * ks + t) * kWStride + g, *wl = s_wlo + (8 * ks + t) * kWStride + g;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t h0 = __float_as_uint(wh[8 * nt]), h1 = __float_as_uint(wh[4 * kWStride + 8 * nt]);
+                const uint32_t l0 = __float_as_uint(wl[8 * nt]), l1 = __float_as_uint(wl[4 * kWStride + 8 * nt]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_tf32(tacc[mt][nt], ahi[mt], h0, h1);
+                    mma_tf32(tacc[mt][nt], alo[mt], h0, h1);
+                    mma_tf32(tacc[mt][nt], ahi[mt], l0, l1);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s = fmaf(acc[r >> 1][nt][2 * (r & 1)], tacc[r >> 1][nt][2 * (r & 1)], s);
+                s = fmaf(acc[r >> 1][nt][2 * (r & 1) + 1], tacc[r >> 1][nt][2 * (r & 1) + 1], s);
+            }
+            gpart[d][r] = s;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        part[r] += __shfl_xor_sync(0xffffffffu, part[r], 1);
+        part[r] += __shfl_xor_sync(0xffffffffu, part[r], 2);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            gpart[d][r] += __shfl_xor_sync(0xffffffffu, gpart[d][r], 1);
+            gpart[d][r] += __shfl_xor_sync(0xffffffffu, gpart[d][r], 2);
+        }
+    }
+    __syncwarp();
+    if (t == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float *o = xs + (8 * r + g) * kXsStride + kXsTmp;
+            o[0] = part[r]; o[1] = gpart[0][r]; o[2] = gpart[1][r]; o[3] = gpart[2][r];
+        }
+    }
+    __syncwarp();
+    const float4 o = *reinterpret_cast<const float4 *>(xs + lane * kXsStride + kXsTmp);
+    grad[0] = o.y; grad[1] = o.z; grad[2] = o.w;
+    return o.x + s_net[kOffB1];
+}
+
 constexpr int kMmaSmemFloats(int warps) { return kNetFloats + 2 * kWRows * kWStride + warps * 32 * kXsStride; }
 
 }  // namespace snb

@@ -141,6 +141,17 @@ class SDFModel:
         call("snb_sdf_eval", x.shape[0], ptr(x), C.byref(net), mode, ptr(out))
         return out.unsqueeze(-1)
 
+    @torch.no_grad()
+    def sdf_and_gradient(self, x: torch.Tensor):
+        """(sdf [n,1], d sdf/dx [n,3]) in one pass -- SDFNetwork.gradient (models/fields.py:107-119) for `ad`
+        normals, forward-mode on the tensor cores instead of an autograd double pass."""
+        x = x.contiguous().float()
+        sdf = torch.empty(x.shape[0], device=x.device)
+        grad = torch.empty(x.shape[0], 3, device=x.device)
+        net = self.net_struct()
+        call("snb_sdf_eval_grad", x.shape[0], ptr(x), C.byref(net), ptr(sdf), ptr(grad))
+        return sdf.unsqueeze(-1), grad
+
     # -- reference checkpoint format (exp_runner.py:298-315) --------------------------------------
     def reference_state_dict(self) -> Dict[str, torch.Tensor]:
         o, s = self._small_offsets(), self.small

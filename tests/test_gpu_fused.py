@@ -17,16 +17,19 @@ pytestmark = pytest.mark.gpu
 ENC = dict(otype="HashGrid", n_levels=6, n_features_per_level=2, log2_hashmap_size=14, base_resolution=8, per_level_scale=1.6)
 
 
-def _conf(n_patches, grad="dfd"):
+ENC16 = dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.4)
+
+
+def _conf(n_patches, grad="dfd", enc=None):
     from supernormal_b200.synthetic import DILIGENT_CONF
-    return dict(DILIGENT_CONF, batch_size=n_patches, encoding=ENC, gradient_method=grad, end_iter=100)
+    return dict(DILIGENT_CONF, batch_size=n_patches, encoding=enc or ENC, gradient_method=grad, end_iter=100)
 
 
-def _setup(cuda, n_patches=96, variance=0.3, n_active=4, seed=0, table_scale=0.02):
+def _setup(cuda, n_patches=96, variance=0.3, n_active=4, seed=0, table_scale=0.02, ENC=ENC):
     from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene
     from supernormal_b200.trainer import FusedTrainer
     ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device="cpu")
-    conf = _conf(n_patches)
+    conf = _conf(n_patches, enc=ENC)
     torch.manual_seed(seed)
     osdf = T.SDFNetwork(ENC, 64, 0.6, fp16=True)
     with torch.no_grad():
@@ -78,6 +81,47 @@ def test_sdf_eval_matches_oracle(cuda):
     assert (got.double() - ref).abs().max() < 2e-5 * max(1.0, ref.abs().max().item())
     occ = tr.model.sdf(x.to(cuda), mode=1).cpu()
     assert torch.allclose(occ.double(), torch.sigmoid(-80 * ref), atol=2e-3)
+
+
+@pytest.mark.parametrize("n_active,enc", [(0, ENC), (1, ENC), (4, ENC), (6, ENC), (13, ENC16), (16, ENC16)])
+def test_sdf_eval_grad_matches_oracle(cuda, n_active, enc):
+    """snb_sdf_eval_grad (sdf + analytic gradient, one pass, tensor cores) against an fp64 MLP on the C oracle's
+    fp16-faithful features and fp32 dy/dx, and against the autograd route of SDFNetwork.gradient
+    (models/fields.py:107-119) on the torch oracle.  Tolerances: sdf 2e-5 abs, gradient 2e-5 * max|grad|."""
+    ds, osdf, odev, orend, tr, _ = _setup(cuda, n_active=n_active, ENC=enc)
+    n = 4133   # not a multiple of the warp / CTA size: ragged tail
+    x = torch.rand(n, 3) * 2 - 1
+    tr.model.prep()
+    sdf, grad = tr.model.sdf_and_gradient(x.to(cuda))
+    sdf, grad = sdf.cpu(), grad.cpu()
+    assert torch.equal(sdf, tr.model.sdf(x.to(cuda)).cpu())   # same value path as snb_sdf_eval
+    feats, dydx = oracle.hashgrid_fwd(osdf.spec, x.numpy(), osdf.encoding_params.detach().numpy().astype(np.float16),
+                                      n_active=osdf.bindwidth, want_dy_dx=True)
+    w0 = (osdf.lin0.weight_g * osdf.lin0.weight_v / osdf.lin0.weight_v.norm(dim=1, keepdim=True)).double()
+    w1 = (osdf.lin1.weight_g * osdf.lin1.weight_v / osdf.lin1.weight_v.norm(dim=1, keepdim=True)).double()
+    xin = torch.cat([x, torch.from_numpy(feats.astype(np.float32))], 1).double()
+    z = xin @ w0.T + osdf.lin0.bias.double()
+    ref_sdf = torch.nn.functional.softplus(z, beta=100) @ w1.T + osdf.lin1.bias.double()
+    jac = torch.cat([torch.eye(3, dtype=torch.float64).expand(n, 3, 3), torch.from_numpy(dydx).double()], 1)   # d x_in / d x  [n, 3+2L, 3]
+    dz = torch.einsum("hk,nkd->nhd", w0, jac)
+    ref_grad = torch.einsum("nh,nhd->nd", torch.sigmoid(100 * z) * w1[0], dz)
+    assert (sdf.double() - ref_sdf).abs().max() < 2e-5 * max(1.0, ref_sdf.abs().max().item())
+    scale = max(1.0, ref_grad.abs().max().item())
+    assert (grad.double() - ref_grad).abs().max() < 2e-5 * scale, (grad.double() - ref_grad).abs().max().item() / scale
+    # autograd route (the reference's own): fp32 expression of the same function
+    ag = osdf.gradient(x.clone())[:, 0].detach()
+    assert (grad - ag).abs().max() < 1e-3 * scale
+
+
+def test_sdf_eval_grad_argument_errors(cuda):
+    import ctypes as C
+    from supernormal_b200 import _lib
+    ds, osdf, odev, orend, tr, _ = _setup(cuda)
+    net = tr.model.net_struct()
+    l = _lib.lib()
+    assert l.snb_sdf_eval_grad(-1, None, C.byref(net), None, None, None) < 0
+    assert l.snb_sdf_eval_grad(8, None, C.byref(net), None, None, None) < 0 and b"null" in l.snb_last_error()
+    assert l.snb_sdf_eval_grad(0, None, C.byref(net), None, None, None) == 0     # empty input is a no-op
 
 
 @pytest.mark.parametrize("variance,cut_active", [(0.3, False), (0.75, True)])
