@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
                                                                  const __half2 *__restrict__ feats,
                                                                  const float *__restrict__ d_sdf0,
                                                                  const float *__restrict__ d_sdf1,
-                                                                 float *__restrict__ table_grad, float *__restrict__ net_grad, int dbg) {
+                                                                 float *__restrict__ table_grad, float *__restrict__ net_grad) {
     extern __shared__ __align__(16) float smem[];
     float *s_net = smem;                      // kNetFloats
     float *s_dz = s_net + kNetFloats;         // kTile * kDzStride
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
         accB1 += ds;
 
         // ---- phase C: d(features) = W0[:,3:]^T dz, scattered to the table with the trilinear weights
-        if (valid && dsdf != 0.f && !(dbg & 2)) {
+        if (valid && dsdf != 0.f) {
             for (uint32_t l = 0; l < n_active; ++l) {
                 const float4 *w0 = reinterpret_cast<const float4 *>(s_net + kOffW0T + (3 + 2 * l) * kH);
                 const float4 *w1 = w0 + kH / 4;
@@ -263,8 +263,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
 #pragma unroll
                 for (uint32_t k = 0; k < 8; ++k) {
                     float w = corner_weight(cell, k);
-                    if (!(dbg & 1)) atomicAdd(gt + corner_index(c, cell, k), make_float2(w * g0, w * g1));
-                    else if (w * g0 == 123.f) atomicAdd(gt + corner_index(c, cell, k), make_float2(w * g0, w * g1));
+                    atomicAdd(gt + corner_index(c, cell, k), make_float2(w * g0, w * g1));
                 }
             }
         }
@@ -301,250 +300,6 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
     }
     atomicAdd(net_grad + kOffW1 + 2 * lane, accW1a);
     atomicAdd(net_grad + kOffW1 + 2 * lane + 1, accW1b);
-    if (lane == 0) atomicAdd(net_grad + kOffB1, accB1);
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward on the tensor cores
-// ---------------------------------------------------------------------------------------------
-// All three contractions of the MLP backward are mma.sync m16n8k8 TF32 with fp32 accumulation and hi/lo-split fp32
-// operands (products exact to 2^-22, see sdf_mma.cuh):
-//   (1) z  = X W0          warp-local [32 pts x K] x [K x 64]          (recompute from the kept fp16 features)
-//   (2) u  = dz W0feat^T   warp-local [32 pts x 64] x [64 x 2L]        (d loss / d features -> table scatter)
-//   (3) dW0 += X^T dz      CTA-wide   [K x P] x [P x 64], P = 32 * warps points per round; the 3 x 8 output tiles are
-//                          dealt to the warps, so the persistent accumulators cost 8 registers per thread instead of 96.
-// dz is handed from the accumulator layout of (1) to the operand layouts of (2)/(3) through a shared-memory tile.
-constexpr int kDzS = 72;        // floats per point row of the dz tile
-
-struct BwdSmem {
-    float *net, *whi, *wlo, *xs, *dz;
-    LevelCtx *lvl;
-};
-
-__global__ void __launch_bounds__(384, 1) sdf_bwd_patch_mma_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
-                                                                   const __half2 *__restrict__ feats,
-                                                                   const float *__restrict__ d_sdf0,
-                                                                   const float *__restrict__ d_sdf1,
-                                                                   float *__restrict__ table_grad, float *__restrict__ net_grad, int dbg) {
-    extern __shared__ __align__(16) float smem[];
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int P = 32 * nwarps;                       // points per CTA round
-    BwdSmem sh;
-    sh.net = smem;
-    sh.whi = sh.net + kNetFloats;
-    sh.wlo = sh.whi + kWRows * kWStride;
-    sh.xs = sh.wlo + kWRows * kWStride;              // [P][kXsStride] (+16 floats of slack for the transposed over-read)
-    sh.dz = sh.xs + P * kXsStride + 16;              // [P][kDzS]
-    sh.lvl = reinterpret_cast<LevelCtx *>(sh.dz + P * kDzS);
-    load_net_to_smem(sh.net, net.net);
-    stage_w_split(sh.net, sh.whi, sh.wlo);
-    if (threadIdx.x < SNB_MAX_LEVELS) sh.lvl[threadIdx.x] = lt.lv[threadIdx.x];
-    __syncthreads();
-
-    const int S = sm.totals[0], E = sm.totals[1];
-    const int64_t M = (int64_t)SNB_PATCH * (S + E);
-    const uint32_t L = net.meta.n_levels, n_active = net.n_active;
-    const int ksteps = (int)(2 * n_active + 7) >> 3;          // feature k-steps of (1) == feature n-tiles of (2)
-    float *xs = sh.xs + warp * 32 * kXsStride;                 // this warp's rows of the staging tile
-    float *dzt = sh.dz + warp * 32 * kDzS;
-
-    // (3): output tiles owned by this warp.  Tile id -> (mt, nt): mt 0,1 = feature columns 0..15 / 16..31, mt 2 = x y z 1.
-    const int n_mt_feat = (int)(2 * n_active + 15) >> 4;
-    const int n_tiles = (n_mt_feat + 1) * 8;
-    float wacc[2][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) wacc[i][c] = 0.f;
-    float accW1[8][2];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) accW1[nt][0] = accW1[nt][1] = 0.f;
-    float accB1 = 0.f;
-
-    for (int64_t round0 = (int64_t)blockIdx.x * P; round0 < M; round0 += (int64_t)gridDim.x * P) {
-        // ---- stage the lane's point: kept features, position, dsdf
-        const int64_t p = round0 + warp * 32 + lane;
-        const bool valid = p < M;
-        float dsdf = 0.f;
-        PointRef r;
-        r.px = r.py = r.pz = 0.f;
-        float *row = xs + lane * kXsStride;
-        if (valid) {
-            r = decode_point(p, S, b, sm);
-            if (!r.is_end) {
-                dsdf = __ldg(d_sdf0 + (int64_t)r.s * SNB_PATCH + r.k);
-                // this start also served as the previous interval's end when that interval had no own end query
-                if (r.s > 0 && __ldg(sm.end_slot + r.s - 1) < 0) dsdf += __ldg(d_sdf1 + (int64_t)(r.s - 1) * SNB_PATCH + r.k);
-            } else {
-                dsdf = __ldg(d_sdf1 + (int64_t)r.s * SNB_PATCH + r.k);
-            }
-            const __half2 *fr = feats + p * L;
-            for (uint32_t l = 0; l < n_active; ++l) *reinterpret_cast<float2 *>(row + 2 * l) = __half22float2(fr[l]);
-        } else {
-            for (uint32_t l = 0; l < n_active; ++l) *reinterpret_cast<float2 *>(row + 2 * l) = make_float2(0.f, 0.f);
-        }
-        for (int c = 2 * (int)n_active; c < 16 * n_mt_feat; ++c) row[c] = 0.f;
-        stage_point(xs, lane, r.px, r.py, r.pz);
-        row[kXsTmp] = dsdf;
-        __syncwarp();
-
-        // ---- (1) z, then dz = dsdf * W1 * sigmoid(100 z) -> shared tile; dW1 / db1 partial sums stay in registers
-        {
-            float acc[2][8][4];
-            warp_layer0_mma(acc, xs, sh.net, sh.whi, sh.wlo, ksteps, lane);
-            float ds[4];
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) ds[rr] = xs[(8 * rr + g) * kXsStride + kXsTmp];
-            if (t == 0) accB1 += (ds[0] + ds[1]) + (ds[2] + ds[3]);
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const float2 w1 = *reinterpret_cast<const float2 *>(sh.net + kOffW1 + 8 * nt + 2 * t);
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    float sp0, sg0, sp1, sg1;
-                    softplus100_both(acc[rr >> 1][nt][2 * (rr & 1)], sp0, sg0);
-                    softplus100_both(acc[rr >> 1][nt][2 * (rr & 1) + 1], sp1, sg1);
-                    accW1[nt][0] = fmaf(ds[rr], sp0, accW1[nt][0]);
-                    accW1[nt][1] = fmaf(ds[rr], sp1, accW1[nt][1]);
-                    *reinterpret_cast<float2 *>(dzt + (8 * rr + g) * kDzS + 8 * nt + 2 * t) = make_float2(ds[rr] * w1.x * sg0, ds[rr] * w1.y * sg1);
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- (2) u = dz W0feat^T  (rows: points, cols: feature pairs) and the table scatter straight from the fragments
-        if (ksteps > 0 && !(dbg & 2)) {
-            float u[2][4][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) u[mt][nt][c] = 0.f;
-#pragma unroll 2
-            for (int ks = 0; ks < 8; ++ks) {
-                uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const float *r0 = dzt + (16 * mt + g) * kDzS + 8 * ks + t;
-                    const float v[4] = {r0[0], r0[8 * kDzS], r0[4], r0[8 * kDzS + 4]};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        ahi[mt][e] = to_tf32(v[e]);
-                        alo[mt][e] = to_tf32(v[e] - __uint_as_float(ahi[mt][e]));
-                    }
-                }
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    if (nt < ksteps) {
-                        // B[k = h][n = feature j] = W0T[3 + j][h]
-                        const float *wh = sh.whi + (8 * nt + g) * kWStride + 8 * ks + t, *wl = sh.wlo + (8 * nt + g) * kWStride + 8 * ks + t;
-                        const uint32_t h0 = __float_as_uint(wh[0]), h1 = __float_as_uint(wh[4]);
-                        const uint32_t l0 = __float_as_uint(wl[0]), l1 = __float_as_uint(wl[4]);
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            mma_tf32(u[mt][nt], ahi[mt], h0, h1);
-                            mma_tf32(u[mt][nt], alo[mt], h0, h1);
-                            mma_tf32(u[mt][nt], ahi[mt], l0, l1);
-                        }
-                    }
-                }
-            }
-            // thread holds, for points 8 rr + g, the feature pair of level 4 nt + t
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const float *prow = xs + (8 * rr + g) * kXsStride;
-                if (prow[kXsTmp] == 0.f) continue;       // dsdf == 0 (also: rows past M)
-                const float px = prow[kXsXyz], py = prow[kXsXyz + 1], pz = prow[kXsXyz + 2];
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const uint32_t l = 4 * nt + t;
-                    if (l < n_active) {
-                        const float g0 = u[rr >> 1][nt][2 * (rr & 1)], g1 = u[rr >> 1][nt][2 * (rr & 1) + 1];
-                        const LevelCtx c = sh.lvl[l];
-                        Cell cell = cell_of(c, px, py, pz);
-                        float2 *gt = reinterpret_cast<float2 *>(table_grad) + c.offset;
-#pragma unroll
-                        for (uint32_t k = 0; k < 8; ++k) {
-                            float w = corner_weight(cell, k);
-                            if (!(dbg & 1)) atomicAdd(gt + corner_index(c, cell, k), make_float2(w * g0, w * g1));
-                            else if (w * g0 == 123.f) atomicAdd(gt + corner_index(c, cell, k), make_float2(w * g0, w * g1));
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (dbg & 4) continue;
-
-        // ---- (3) dW0T[col][h] += sum over the round's P points of x[p][col] * dz[p][h]
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int tile = warp + i * nwarps;
-            if (tile < n_tiles) {
-                const int mtf = tile >> 3, nt = tile & 7;
-                const bool xyz = mtf == n_mt_feat;                       // last m-tile: x y z 1 (fp32, needs its own hi/lo split)
-                const int col0 = xyz ? kXsXyz : 16 * mtf;
-                for (int ks = 0; ks < 4 * nwarps; ++ks) {
-                    // A[m = column][k = point] read transposed from the staging tile; B[k = point][n = h] from the dz tile
-                    const float *xa = sh.xs + (8 * ks + t) * kXsStride + col0 + g;
-                    const float av[4] = {xa[0], xa[8], xa[4 * kXsStride], xa[4 * kXsStride + 8]};
-                    const float *db = sh.dz + (8 * ks + t) * kDzS + 8 * nt + g;
-                    const float bv0 = db[0], bv1 = db[4 * kDzS];
-                    uint32_t a[4], bh0 = to_tf32(bv0), bh1 = to_tf32(bv1);
-                    const uint32_t bl0 = to_tf32(bv0 - __uint_as_float(bh0)), bl1 = to_tf32(bv1 - __uint_as_float(bh1));
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) a[e] = xyz ? to_tf32(av[e]) : __float_as_uint(av[e]);
-                    mma_tf32(wacc[i], a, bh0, bh1);
-                    mma_tf32(wacc[i], a, bl0, bl1);
-                    if (xyz) {
-                        uint32_t al[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) al[e] = to_tf32(av[e] - __uint_as_float(a[e]));
-                        mma_tf32(wacc[i], al, bh0, bh1);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- flush
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int tile = warp + i * nwarps;
-        if (tile < n_tiles) {
-            const int mtf = tile >> 3, nt = tile & 7;
-            const bool xyz = mtf == n_mt_feat;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int rowi = g + 8 * (c >> 1), h = 8 * nt + 2 * t + (c & 1);
-                float *dst = nullptr;
-                if (xyz) {
-                    if (rowi < 3) dst = net_grad + kOffW0T + rowi * kH + h;
-                    else if (rowi == 3) dst = net_grad + kOffB0 + h;
-                } else {
-                    const int j = 16 * mtf + rowi;
-                    if (j < 2 * (int)n_active) dst = net_grad + kOffW0T + (3 + j) * kH + h;
-                }
-                if (dst) atomicAdd(dst, wacc[i][c]);
-            }
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            float v = accW1[nt][e];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (g == 0) atomicAdd(net_grad + kOffW1 + 8 * nt + 2 * t + e, v);
-        }
-    accB1 += __shfl_xor_sync(0xffffffffu, accB1, 4);
-    accB1 += __shfl_xor_sync(0xffffffffu, accB1, 8);
-    accB1 += __shfl_xor_sync(0xffffffffu, accB1, 16);
     if (lane == 0) atomicAdd(net_grad + kOffB1, accB1);
 }
 
@@ -632,22 +387,12 @@ extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *ne
     SNB_REQUIRE(feats && d_sdf0 && d_sdf1 && table_grad && net_grad, SNB_ERR_NULL, "sdf_bwd_patch: null buffer");
     SNB_REQUIRE(aligned(table_grad, 8), SNB_ERR_ALIGN, "sdf_bwd_patch: table_grad must be 8-byte aligned");
     static const size_t smem = sizeof(float) * (kNetFloats + kTile * kDzStride + kTile * kXStride);
-    static const int dbg = getenv("SNB_BWD_DBG") ? atoi(getenv("SNB_BWD_DBG")) : 0;   // timing experiments only: 1 no atomics, 2 no phase (2), 4 no phase (3)
-    static const int bwd_warps = getenv("SNB_BWD_WARPS") ? atoi(getenv("SNB_BWD_WARPS")) : 12;   // 0: scalar-FMA kernel (cross-checks)
-    static const size_t smem_mma = sizeof(float) * (kNetFloats + 2 * kWRows * kWStride + 32 * bwd_warps * (kXsStride + kDzS) + 16) + sizeof(LevelCtx) * SNB_MAX_LEVELS;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(sdf_bwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(sdf_bwd_patch_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
         configured = true;
     }
-    if (bwd_warps > 0) {
-        SNB_REQUIRE(bwd_warps <= 12 && bwd_warps >= 2, SNB_ERR_ARG, "sdf_bwd_patch: SNB_BWD_WARPS must be in [2, 12]");
-        const int ctas_per_sm = smem_mma <= 110 * 1024 ? 2 : 1;
-        sdf_bwd_patch_mma_kernel<<<kNumSMs * ctas_per_sm, 32 * bwd_warps, smem_mma, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad, dbg);
-    } else {
-        sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad, dbg);
-    }
+    sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
     SNB_LAUNCH_CHECK("sdf_bwd_patch");
     return SNB_OK;
 }

@@ -92,6 +92,21 @@ def chamfer_distance_and_f1_score(ref_points: np.ndarray, eval_points: np.ndarra
     return float(cd), float(2 * precision * recall / (precision + recall))
 
 
+def evaluate_sphere_mesh(v: np.ndarray, t: np.ndarray, radius: float, world_scale: float = 100.0) -> dict:
+    """Chamfer distance / F-score (models/cd_and_fscore.py:5-29) of a mesh against the analytic sphere, both sampled
+    with 200 000 points (area-weighted on the mesh); world_scale maps normalised units to 'mm'."""
+    rng = np.random.RandomState(0)
+    gt = rng.randn(200000, 3)
+    gt = gt / np.linalg.norm(gt, axis=1, keepdims=True) * radius * world_scale
+    p = v[t.astype(np.int64)] * world_scale
+    area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
+    pick = rng.choice(len(t), 200000, p=area / area.sum())
+    uvw = rng.dirichlet([1, 1, 1], 200000)
+    ev = (p[pick] * uvw[:, :, None]).sum(1)
+    cd, f = chamfer_distance_and_f1_score(gt, ev, 0.5)
+    return dict(chamfer_mm=cd, fscore=f, radius_mean=float(np.linalg.norm(v, axis=1).mean()), radius_std=float(np.linalg.norm(v, axis=1).std()))
+
+
 def time_to_mesh(dataset, conf: dict, resolution: int = 512, device="cuda", seed: int = 0, world_scale: float = 100.0,
                  evaluate: bool = True) -> dict:
     """Train conf['end_iter'] iterations from random init, then extract the mesh (BASELINE.json 'time-to-mesh').
@@ -117,18 +132,7 @@ def time_to_mesh(dataset, conf: dict, resolution: int = 512, device="cuda", seed
     v, t = res
     out.update(n_vertices=int(v.shape[0]), n_triangles=int(t.shape[0]))
     if evaluate and rank == 0:
-        r = float(dataset.scene.radius)
-        rng = np.random.RandomState(0)
-        gt = rng.randn(200000, 3)
-        gt = gt / np.linalg.norm(gt, axis=1, keepdims=True) * r * world_scale
-        # area-weighted samples of the extracted mesh
-        p = v[t.astype(np.int64)] * world_scale
-        area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
-        pick = rng.choice(len(t), 200000, p=area / area.sum())
-        uvw = rng.dirichlet([1, 1, 1], 200000)
-        ev = (p[pick] * uvw[:, :, None]).sum(1)
-        cd, f = chamfer_distance_and_f1_score(gt, ev, 0.5)
-        out.update(chamfer_mm=cd, fscore=f, radius_mean=float(np.linalg.norm(v, axis=1).mean()), radius_std=float(np.linalg.norm(v, axis=1).std()))
+        out.update(evaluate_sphere_mesh(v, t, float(dataset.scene.radius), world_scale))
         out.update(eval_mae(tr))
     out["vertices"], out["triangles"] = v, t
     return out

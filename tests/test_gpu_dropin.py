@@ -72,3 +72,51 @@ def test_dropin_trains(cuda):
             first = loss
         last = loss
     assert np.isfinite(last) and last < first
+
+
+def test_fused_rendered_normals_within_1e3_rad_of_reference_path(cuda):
+    """North-star tolerance: rendered normals within 1e-3 rad mean angular error per step.  The reference-shaped step
+    (unmodified reference nerfacc kernels) trains a few iterations; its weights, occupancy grid, patch batch and
+    stratified jitter are then handed to the fused B200 kernels and the two rendered normal maps are compared."""
+    import math
+    from oracle import cuda_path as cp
+    from supernormal_b200.runner import render_patches
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer
+    if cp.load_ref_nerfacc() is None:
+        pytest.skip("oracle/_ref/nerfacc_ref_C.so not built")
+    ds = SyntheticDataset(SyntheticScene(n_views=4, H=64, W=80, exclude_views=(0,)), device=cuda)
+    conf = dict(DILIGENT_CONF, batch_size=512, end_iter=60, increase_bindwidth_every=5, warm_up_end=5)
+    ref = cp.CudaTrainer(ds, conf, backend="reference", seed=0, device=cuda)
+    torch.manual_seed(0)
+    for _ in range(40):
+        ref.step()
+    assert ref.sdf.bindwidth >= 8
+    sd = {"sdf_network_fine": {"encoding.params": ref.sdf.encoding.params.detach(), "lin0.bias": ref.sdf.lin0.bias.detach(),
+                               "lin0.weight_g": ref.sdf.lin0.weight_g.detach(), "lin0.weight_v": ref.sdf.lin0.weight_v.detach(),
+                               "lin1.bias": ref.sdf.lin1.bias.detach(), "lin1.weight_g": ref.sdf.lin1.weight_g.detach(),
+                               "lin1.weight_v": ref.sdf.lin1.weight_v.detach()},
+          "variance_network_fine": {"variance": ref.dev.variance.detach()}}
+    tr = FusedTrainer(ds, conf, device=cuda)
+    tr.model.load_reference_state_dict(sd)
+    tr.model.n_active = ref.sdf.bindwidth
+    tr.grid._binary = ref.renderer.occupancy_grid.binary.clone()
+    o, d, pn, vinv, nrm, msk = ds.gen_random_patches(512, 3, 3, np_rng=np.random.RandomState(3))
+    near, far = ds.near_far_from_sphere(o[:, 1, 1], d[:, 1, 1])
+    step = float(ref.renderer.sampling_step_size)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        out = ref.renderer.render(o, d, pn, near, far, vinv)
+    torch.manual_seed(11)
+    jitter = torch.rand_like(near)               # the draw ray_marching(stratified=True) made (NA/ray_marching.py:158)
+    batch = dict(rays_o=o[:, 1, 1].contiguous(), rays_d=d.view(-1, 9, 3), plane_n=pn, near=near.contiguous(), far=far.contiguous(),
+                 v_inv=vinv.view(-1, 9, 9))
+    comp, wsum = render_patches(tr, batch, np.float32(step), jitter)
+    # same marched + visibility-filtered samples (up to samples whose transmittance sits within ulps of the 1e-8 cut)
+    assert abs(tr.loss_terms()["n_samples"] - out["n_samples"]) <= 2
+    a, b = comp.reshape(-1, 3).double(), out["comp_normal"].reshape(-1, 3).double()
+    hit = (out["weight_sum"].reshape(-1) > 0.5) & (msk.reshape(-1) > 0.5)
+    assert hit.sum() > 500
+    ang = torch.atan2(torch.linalg.cross(a[hit], b[hit]).norm(dim=-1), (a[hit] * b[hit]).sum(-1))   # fp64: arccos cannot resolve 1e-4 rad in fp32
+    assert ang.mean().item() < 1e-3, ang.mean().item()
+    assert torch.allclose(wsum.reshape(-1)[hit], out["weight_sum"].reshape(-1)[hit], atol=2e-3)
