@@ -17,18 +17,89 @@ namespace snb {
 // Empty space.  In the reference an unoccupied probe at t_mid jumps to the first point of the lattice
 //     t_mid (+) dt (+) dt (+) ...            ((+) = one rounded fp32 add, advance_to_next_voxel's do-while)
 // at or beyond the voxel exit, so EVERY point the serial marcher visits in an empty stretch lies on that one
-// lattice.  A warp therefore evaluates 32 consecutive lattice points at once -- lane k replays k adds, probes the
-// grid and runs the reference's own skip arithmetic as if it were visited -- and then follows the visited chain
-// 0 -> 0+J(0) -> ... with shuffles: the per-voxel dependent load + division chain of the serial marcher becomes
-// one parallel step plus a few ~30-cycle hops, and the visited points, hence the emitted samples, are bit-identical.
-__global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b, snb_net net, LevelTable lt, const float *__restrict__ roi,
-                                                            int3 res, const uint8_t *__restrict__ grid, float step,
-                                                            const float *__restrict__ jitter, float eps, snb_samples sm) {
+// lattice.  The CTA therefore evaluates 32 W consecutive lattice points at once -- thread k takes the point after
+// k adds (closed form, march_common.cuh), probes the grid and runs the reference's own skip arithmetic as if it
+// were visited -- and then follows the visited chain 0 -> 0+J(0) -> ... through shared memory: the per-voxel
+// dependent load + division chain of the serial marcher becomes one parallel step plus a few ~30-cycle hops, and
+// the visited points, hence the emitted samples, are bit-identical.
+//
+// Occupied stretches.  W warps of a CTA own ONE ray.  A lone warp needs ~40 k cycles for the SDF of a 31-sample batch at
+// 14 levels (in-order issue: it cannot overlap its own gathers with its own MLP), and the longest rays chain 10-20 such
+// batches while the SM idles (measured per-ray with clock64; profiles/README.md).  So the batch's 32 points are
+// evaluated by the whole CTA: warp w gathers and blends levels w, w+W, ... into a shared feature tile, then computes
+// hidden units [64 w / W, 64 (w+1) / W) of the MLP for all 32 points; the partial sums meet in shared memory.  No work
+// is duplicated or speculated; the batch latency drops ~W-fold.  Control state (t0, t1, t_mid, T, j, ...) is kept
+// redundantly in every thread, so the control flow is CTA-uniform and the barriers are unconditional.
+constexpr int kFeatStride = 2 * SNB_MAX_LEVELS + 1;   // odd: conflict-free row-per-lane reads
+
+// SDF of the warp-lane's point, computed cooperatively by the W warps of the CTA (all threads must call; every warp
+// passes the same 32 points).  s_feat: [32][kFeatStride], s_part: [W][32].
+template <int W>
+__device__ __forceinline__ float cta_sdf(bool valid, float x, float y, float z, const __half2 *__restrict__ table, const LevelCtx *lvl,
+                                         uint32_t n_active, const float *s_net, float *s_feat, float *s_part, int warp, int lane) {
+    constexpr int HU = kH / W;   // hidden units per warp
+    for (uint32_t l = warp; l < n_active; l += W) {
+        float2 ff = make_float2(0.f, 0.f);
+        if (valid) {
+            const LevelCtx c = lvl[l];
+            Cell cell = cell_of(c, x, y, z);
+            ff = __half22float2(interp_level(c, cell, table));
+        }
+        s_feat[lane * kFeatStride + 2 * l] = ff.x;
+        s_feat[lane * kFeatStride + 2 * l + 1] = ff.y;
+    }
+    __syncthreads();
+    const int h0 = HU * warp;
+    float acc[HU];
+#pragma unroll
+    for (int q = 0; q < HU / 4; ++q) {
+        const float4 bq = *reinterpret_cast<const float4 *>(s_net + kOffB0 + h0 + 4 * q);
+        acc[4 * q] = bq.x; acc[4 * q + 1] = bq.y; acc[4 * q + 2] = bq.z; acc[4 * q + 3] = bq.w;
+    }
+    const float xin[3] = {x, y, z};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int q = 0; q < HU / 4; ++q) {
+            const float4 wq = *reinterpret_cast<const float4 *>(s_net + kOffW0T + r * kH + h0 + 4 * q);
+            acc[4 * q] = fmaf(wq.x, xin[r], acc[4 * q]); acc[4 * q + 1] = fmaf(wq.y, xin[r], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(wq.z, xin[r], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wq.w, xin[r], acc[4 * q + 3]);
+        }
+    }
+    const float *frow = s_feat + lane * kFeatStride;
+    for (uint32_t jf = 0; jf < 2 * n_active; ++jf) {
+        const float v = frow[jf];
+        const float *wr = s_net + kOffW0T + (3 + jf) * kH + h0;
+#pragma unroll
+        for (int q = 0; q < HU / 4; ++q) {
+            const float4 wq = *reinterpret_cast<const float4 *>(wr + 4 * q);
+            acc[4 * q] = fmaf(wq.x, v, acc[4 * q]); acc[4 * q + 1] = fmaf(wq.y, v, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(wq.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wq.w, v, acc[4 * q + 3]);
+        }
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < HU; ++i) part = fmaf(s_net[kOffW1 + h0 + i], softplus100<false>(acc[i]), part);
+    s_part[warp * 32 + lane] = part;
+    __syncthreads();
+    float s = s_net[kOffB1];
+#pragma unroll
+    for (int w = 0; w < W; ++w) s += s_part[w * 32 + lane];
+    return s;
+}
+
+template <int W, int MB>
+__global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_batch b, snb_net net, LevelTable lt, const float *__restrict__ roi,
+                                                                       int3 res, const uint8_t *__restrict__ grid, float step,
+                                                                       const float *__restrict__ jitter, float eps, snb_samples sm) {
     __shared__ __align__(16) float s_net[kNetFloats];
+    __shared__ float s_land[32 * W], s_tm[32 * W];
+    __shared__ int s_J[32 * W];
+    __shared__ float s_feat[32 * kFeatStride], s_part[32 * W];
     load_net_to_smem(s_net, net.net);
     const LevelCtx *s_lvl = lt.lv;
-    const int lane = threadIdx.x & 31;
-    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ray = blockIdx.x;
     if (ray >= b.n_patches) return;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const float inv_s = s_net[kOffInvS];
@@ -56,29 +127,42 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
 
     while (t_mid < far) {
         if (!occ_mode) {
-            // ---- speculative window over 32 lattice points of the empty-space lattice
-            float tm = t_mid;
-            for (int s = 0; s < lane; ++s) tm = __fadd_rn(tm, step);
+            // ---- speculative window over 32 W points of the empty-space lattice
+            const int idx = 32 * warp + lane;
+            AddChain ch = make_add_chain(t_mid, step);
+            float tm;
+            if (add_chain_at(ch, 32u * W - 1u, tm)) {   // the closed form covers the last point of the window, hence all of it
+                add_chain_at(ch, (uint32_t)idx, tm);
+            } else {                                    // serial replay
+                ch.Q = 0u;
+                tm = t_mid;
+                for (int s = 0; s < idx; ++s) tm = __fadd_rn(tm, step);
+            }
             const bool inr = tm < far;
             const float px = __fmaf_rn(tm, d[0], o[0]), py = __fmaf_rn(tm, d[1], o[1]), pz = __fmaf_rn(tm, d[2], o[2]);
             const bool occ = inr && march_occupied(rc, px, py, pz, grid);
             int J = 1;
             float land = tm;
-            if (inr && !occ) land = march_skip_count(rc, tm, step, px, py, pz, d, inv_d, far, J);
-            const unsigned occ_mask = __ballot_sync(kAll, occ), inr_mask = __ballot_sync(kAll, inr);
-            int cur = 0;
-            float last_land = t_mid;
+            if (inr && !occ) land = march_skip_count_fast(rc, ch, ch.T0 + (uint32_t)idx * ch.Q, tm, step, px, py, pz, d, inv_d, far, J);
+            s_land[idx] = land;
+            s_tm[idx] = tm;
+            s_J[idx] = !inr ? -1 : (occ ? 0 : J);   // hop length; 0: occupied, -1: beyond far
+            __syncthreads();
+            int cur = 0, prev = -1;
             bool done = false, found = false;
-            while (cur < 32) {
-                if (!((inr_mask >> cur) & 1u)) { done = true; break; }
-                if ((occ_mask >> cur) & 1u) { found = true; break; }
-                last_land = __shfl_sync(kAll, land, cur);
-                cur += __shfl_sync(kAll, J, cur);
+            while (cur < 32 * W) {
+                const int c = s_J[cur];
+                if (c <= 0) { done = c < 0; found = c == 0; break; }
+                prev = cur;
+                cur += c;
             }
+            const float last_land = prev >= 0 ? s_land[prev] : t_mid;
+            const float tm_found = found ? s_tm[cur] : 0.f;
+            __syncthreads();   // the window arrays are rewritten by the next window
             if (done) break;
             if (found) {
                 if (cur > 0) {   // reached by a skip: t0/t1 are re-centred on t_mid (CS/ray_marching.cu:173-174)
-                    t_mid = __shfl_sync(kAll, tm, cur);
+                    t_mid = tm_found;
                     t0 = __fmaf_rn(step, -0.5f, t_mid);
                     t1 = __fmaf_rn(step, 0.5f, t_mid);
                     chain_open = false;
@@ -92,25 +176,35 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
             chain_open = false;
             continue;
         }
-        // ---- occupied stretch: 31 candidate samples on the lattice t0 (+) dt (+) ...; lane 0 is known to be occupied
+        // ---- occupied stretch: 31 candidate samples on the lattice t0, t1, t1 (+) dt, ...; candidate 0 is known to be occupied.
+        // Every warp holds the same batch: lane i spans [l0, l1] = [t1 after i-1 adds, t1 after i adds] (i = 0: [t0, t1]).
         float l0 = t0, l1 = t1;
-        for (int s = 0; s < lane; ++s) {
-            l0 = l1;
-            l1 = __fadd_rn(l0, step);
+        {
+            const AddChain c1 = make_add_chain(t1, step);
+            float a = t1, bprev = t0;
+            bool okc = add_chain_at(c1, (uint32_t)lane, a);
+            if (lane > 0) okc = add_chain_at(c1, (uint32_t)lane - 1u, bprev) && okc;
+            if (__all_sync(kAll, okc)) {
+                l1 = a;
+                l0 = bprev;
+            } else {
+                for (int s = 0; s < lane; ++s) {
+                    l0 = l1;
+                    l1 = __fadd_rn(l0, step);
+                }
+            }
         }
-        float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
-        float px = __fmaf_rn(lm, d[0], o[0]), py = __fmaf_rn(lm, d[1], o[1]), pz = __fmaf_rn(lm, d[2], o[2]);
-        bool in_range = lm < far;
-        bool occ = (lane < 31) && in_range && march_occupied(rc, px, py, pz, grid);
-        unsigned stop = ~__ballot_sync(kAll, occ);  // bit 31 always set: lane 31 only evaluates an end point
-        int f = __ffs(stop) - 1;                    // lanes [0,f) are samples, 1 <= f <= 31
+        const float lm = (lane == 0) ? t_mid : __fmul_rn(__fadd_rn(l0, l1), 0.5f);
+        const float px = __fmaf_rn(lm, d[0], o[0]), py = __fmaf_rn(lm, d[1], o[1]), pz = __fmaf_rn(lm, d[2], o[2]);
+        const bool in_range = lm < far;
+        const bool occ = (lane < 31) && in_range && march_occupied(rc, px, py, pz, grid);
+        const unsigned stop = ~__ballot_sync(kAll, occ);  // bit 31 always set: lane 31 only evaluates an end point
+        const int f = __ffs(stop) - 1;                    // lanes [0,f) are samples, 1 <= f <= 31
         // SDF at the start of every sample and (lane f) at the end of the last one; positions as the
         // reference builds them: t_origins + t_dirs * t (models/renderer.py:84-86), separately rounded
-        float sdf = 0.f;
-        if (lane <= f)
-            sdf = sdf_point<false, false>(__fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
-                                   __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, s_lvl, net.n_active, s_net, nullptr);
-        float sdf_next = __shfl_down_sync(kAll, sdf, 1);
+        const float sdf = cta_sdf<W>(lane <= f, __fadd_rn(o[0], __fmul_rn(d[0], l0)), __fadd_rn(o[1], __fmul_rn(d[1], l0)),
+                                     __fadd_rn(o[2], __fmul_rn(d[2], l0)), table, s_lvl, net.n_active, s_net, s_feat, s_part, warp, lane);
+        const float sdf_next = __shfl_down_sync(kAll, sdf, 1);
         float fac = lane < f ? __fsub_rn(1.f, neus_alpha(sdf, sdf_next, inv_s)) : 1.f;
         // transmittance in front of every candidate: T * prod_{i<lane} (1 - alpha_i); NA/vol_rendering.py:730-748 keeps T >= eps
 #pragma unroll
@@ -118,9 +212,9 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
             float u = __shfl_up_sync(kAll, fac, off);
             if (lane >= off) fac *= u;
         }
-        float excl = __shfl_up_sync(kAll, fac, 1);
-        float Tb = lane == 0 ? T : T * excl;
-        unsigned invisible = __ballot_sync(kAll, lane < f && !(Tb >= eps));
+        const float excl = __shfl_up_sync(kAll, fac, 1);
+        const float Tb = lane == 0 ? T : T * excl;
+        const unsigned invisible = __ballot_sync(kAll, lane < f && !(Tb >= eps));
         int nvis = invisible ? __ffs(invisible) - 1 : f;
         T = __shfl_sync(kAll, T * fac, f - 1);
         bool ray_done = nvis < f;
@@ -129,7 +223,7 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
             overflow = true;
             ray_done = true;
         }
-        if (lane < nvis) {
+        if (warp == 0 && lane < nvis) {
             sc0[j + lane] = l0;
             sc1[j + lane] = l1;
         }
@@ -150,7 +244,7 @@ __global__ void __launch_bounds__(128, 4) march_visible_kernel(snb_patch_batch b
         occ_mode = false;
         chain_open = false;
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         sm.counts[ray] = j;
         sm.end_counts[ray] = runs;
         if (overflow) atomicExch(sm.totals + 2, 1);
@@ -264,7 +358,8 @@ extern "C" int32_t snb_march_visible(const snb_patch_batch *b, const snb_net *ne
     SNB_REQUIRE(sm->counts && sm->end_counts && sm->totals && sm->scratch_t0 && sm->scratch_t1 && sm->scratch_stride > 0, SNB_ERR_NULL, "march_visible: null scratch");
     SNB_REQUIRE(aligned(net->net, 16), SNB_ERR_ALIGN, "march_visible: net must be 16-byte aligned");
     cudaMemsetAsync(sm->totals, 0, 4 * sizeof(int32_t), S(stream));
-    march_visible_kernel<<<(unsigned)cdiv(b->n_patches, 4), 128, 0, S(stream)>>>(*b, *net, make_level_table(net->meta), roi, make_int3(rx, ry, rz), grid, step, jitter, eps, *sm);
+    // CTA per ray, 4 warps, compiled for 6 CTAs per SM (80 registers): measured best of W in {1,2,4,8} x {4,6,8} CTAs/SM over the schedule
+    march_visible_kernel<4, 6><<<(unsigned)b->n_patches, 128, 0, S(stream)>>>(*b, *net, make_level_table(net->meta), roi, make_int3(rx, ry, rz), grid, step, jitter, eps, *sm);
     SNB_LAUNCH_CHECK("march_visible");
     return SNB_OK;
 }

@@ -98,4 +98,76 @@ __device__ __forceinline__ float march_skip_count(const RoiCtx &c, float t_mid, 
     return t;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Closed form of the reference's repeated rounded adds  t (+) dt (+) dt ...  (advance_to_next_voxel's do-while and
+// the t0/t1 stepping of the march loop).  While the run stays inside the binade of its base value, every t is an
+// integer multiple T of u = ulp(base), and one rounded add maps T to rne(T + dt/u) = T + rne(dt/u): the same integer
+// increment Q every time -- unless dt/u has a fractional part of exactly 1/2, where round-half-even would depend on
+// the parity of T.  Then: value after k adds = (T0 + k Q) u, and the number of adds the do-while performs to reach
+// t_target is max(1, ceil((T_target - T) / Q)) -- integer arithmetic, bit-identical to replaying the adds.
+// Q == 0 marks "closed form not available" (base not a positive normal, tie case, dt outside [u, 2^22 u]); callers then
+// replay the adds serially, as they do when a run leaves the binade.
+struct AddChain {
+    uint32_t T0;   // 24-bit significand of the base (hidden bit set)
+    uint32_t hi;   // exponent bits of the base, in place
+    uint32_t Q;    // significand increment per add; 0: unavailable
+};
+
+__device__ __forceinline__ AddChain make_add_chain(float base, float dt) {
+    AddChain c;
+    const uint32_t b = __float_as_uint(base), e = b >> 23;   // callers pass base > 0: sign bit clear
+    c.T0 = (b & 0x007fffffu) | 0x00800000u;
+    c.hi = e << 23;
+    c.Q = 0;
+    const int sh = 150 - (int)e;                              // dt / u = dt * 2^sh
+    if (!(base > 0.f) || e == 0u || e >= 255u || sh > 127 || sh < -126) return c;
+    const float D = __fmul_rn(dt, __uint_as_float((uint32_t)(sh + 127) << 23));   // exact: power-of-two scaling
+    if (!(D >= 1.f && D <= 4194304.f)) return c;
+    const float Di = floorf(D), f = __fsub_rn(D, Di);         // exact: D < 2^23
+    if (f == 0.5f) return c;
+    c.Q = (uint32_t)Di + (f > 0.5f ? 1u : 0u);
+    return c;
+}
+
+// value after k adds; false when the closed form does not apply (caller falls back to the serial replay)
+__device__ __forceinline__ bool add_chain_at(const AddChain &c, uint32_t k, float &out) {
+    const uint64_t T = (uint64_t)c.T0 + (uint64_t)k * c.Q;
+    if (c.Q == 0u || T >= 0x01000000ull) return false;
+    out = __uint_as_float(c.hi | ((uint32_t)T & 0x007fffffu));
+    return true;
+}
+
+// do { t += dt; ++n; } while (t < t_target) starting from the chain point with significand T; false -> fall back
+__device__ __forceinline__ bool add_chain_skip(const AddChain &c, uint32_t T, float t_target, float &t_out, int &n_out) {
+    const uint32_t tb = __float_as_uint(t_target);
+    if (c.Q == 0u || (tb & 0xff800000u) != c.hi) return false;   // other binade, negative, inf or NaN target
+    const uint32_t TT = (tb & 0x007fffffu) | 0x00800000u;
+    uint32_t n = TT > T ? (TT - T + c.Q - 1u) / c.Q : 1u;
+    if (n == 0u) n = 1u;
+    const uint64_t Tl = (uint64_t)T + (uint64_t)n * c.Q;
+    if (Tl >= 0x01000000ull) return false;
+    t_out = __uint_as_float(c.hi | ((uint32_t)Tl & 0x007fffffu));
+    n_out = (int)n;
+    return true;
+}
+
+// march_skip_count with the closed form when it applies (T = significand of t_mid on chain c)
+__device__ __forceinline__ float march_skip_count_fast(const RoiCtx &c, const AddChain &ch, uint32_t T, float t_mid, float dt_min, float px,
+                                                       float py, float pz, const float *d, const float *inv_d, float far, int &steps) {
+    float tx = march_axis_dist(c, 0, px, d[0], inv_d[0]);
+    float ty = march_axis_dist(c, 1, py, d[1], inv_d[1]);
+    float tz = march_axis_dist(c, 2, pz, d[2], inv_d[2]);
+    float t_target = fminf(__fadd_rn(t_mid, fmaxf(fminf(fminf(tx, ty), tz), 0.0f)), far);
+    float t;
+    if (add_chain_skip(ch, T, t_target, t, steps)) return t;
+    t = t_mid;
+    int n = 0;
+    do {
+        t = __fadd_rn(t, dt_min);
+        ++n;
+    } while (t < t_target);
+    steps = n;
+    return t;
+}
+
 }  // namespace snb
