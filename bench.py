@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=10 ** 9, help="cap on the e2e arm's steps (default: same K)")
+    ap.add_argument("--flush-l2", action="store_true", help="time every step separately and overwrite a 512 MB buffer between steps (cold L2)")
     ap.add_argument("--ref-cuda-steps", type=int, default=100, help="steps of the reference-shaped CUDA path timed beside ours at N=1 (0 = skip)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -185,14 +186,27 @@ def main():
         ev0.record()
         Kr = min(K, args.ref_cuda_steps) if world == 1 else 0
         evr = torch.cuda.Event(enable_timing=True)
+        flush_ms = 0.0
+        if args.flush_l2:
+            junk = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+            pairs = []
         for i in range(K):
+            if args.flush_l2:
+                junk.fill_(i & 0xff)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
             tr.train_step()
+            if args.flush_l2:
+                b_.record()
+                pairs.append((a, b_))
             if i + 1 == Kr:
                 evr.record()   # our time over the same schedule window the reference-shaped path is timed on
         ev1.record()
         barrier()
         torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
+    if args.flush_l2:
+        ms = sum(a.elapsed_time(b_) for a, b_ in pairs)   # steps only; the flush writes between them are not counted
     launches = _lib.LAUNCH_COUNT
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -207,26 +221,26 @@ def main():
     # ---- e2e: the same schedule window [W, W+Ke) on a fresh trainer, every step's patch batch copied from pinned HOST
     # memory inside the timed region and the loss terms read back every step ------------------------------------
     Ke = min(args.e2e_steps, K)
-    pool = [{k: v.cpu().pin_memory() for k, v in tr.sample_batch().items()} for _ in range(16)]
-    h2d = sum(v.numel() * v.element_size() for v in pool[0].values()) + tr.n_patches * 4
-    jit_pool = [torch.rand(tr.n_patches).pin_memory() for _ in range(16)]
+    pool = [{k: v.cpu() for k, v in tr.sample_batch().items()} for _ in range(16)]     # HOST batches (a CPU loader's output)
+    jit_pool = [torch.rand(tr.n_patches) for _ in range(16)]
     te = FusedTrainer(ds, dict(DILIGENT_CONF), device=dev, seed=0, world_size=world, rank=rank)
     for _ in range(W):
         te.train_step()
+    feeder = te.host_feeder(depth=3, log_capacity=max(Ke, 1))
+    h2d, d2h = feeder.h2d_bytes, feeder.d2h_bytes
+    packed = [feeder.pack(pool[i], jit_pool[i]) for i in range(16)]   # the loader's output: packed batches in pinned host memory
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d2h = 0
     barrier()
     e0.record()
+    feeder.submit(packed[0])
     for i in range(Ke):
-        hb = pool[i % 16]
-        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        jit = jit_pool[i % 16].to(dev, non_blocking=True)
-        te.train_step(batch=batch, jitter=jit)
-        st = te.buf.stats.cpu()
-        tot = te.buf.totals.cpu()
-        d2h = st.numel() * 4 + tot.numel() * 4
+        feeder.step()                                                   # launches step i (+ async D2H of its loss terms)
+        if i + 1 < Ke:
+            feeder.submit(packed[(i + 1) % 16])                         # H2D of batch i+1 overlaps step i's kernels
     e1.record()
     barrier()
+    e2e_losses = feeder.losses()
+    assert len(e2e_losses) == Ke and all(np.isfinite(l["loss"]) for l in e2e_losses), "e2e arm produced a non-finite loss"
     ems = e0.elapsed_time(e1)
     t = torch.tensor([ems], device=dev)
     if world > 1:
@@ -238,10 +252,14 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "patches_per_gpu": tr.n_patches, "parallelism": f"dp{world}",
-                           "l2_policy": "per-step working set (hash table 24 MB fp16 + 47 MB fp32 master/grad/Adam state sweep) exceeds nothing by design: inputs change every step (new random patches), Adam sweeps 330 MB > L2 between steps",
+                           "l2_policy": ("flushed: 512 MB overwritten between steps, every step timed separately with CUDA events" if args.flush_l2 else
+                                         "not flushed: a training run is a dependent chain of steps -- parameters are rewritten and patches are new random draws every step, "
+                                         "so no step repeats an input; the fp16 hash table (<= 24 MB) staying L2-resident across steps is part of the design (--flush-l2 times the cold-L2 case)"),
                            "final_iter": tr.iter_step, "samples_per_ray_last": lt["samples_per_ray"], "loss_last": lt["loss"]},
                 "clocks": clk.summary(), "gpu_launches": launches,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                        "how": "HostBatchFeeder: packed batch in pinned host memory -> one H2D copy per step on a copy stream (double-buffered), loss terms D2H every step into a pinned ring",
+                        "loss_last": e2e_losses[-1]["loss"] if e2e_losses else None},
                 "kernels": prof}
         if prof.get("dominant"):
             dk = prof["dominant"]

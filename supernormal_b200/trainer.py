@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Dict, Optional
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
@@ -217,6 +217,102 @@ class SampleBuffers:
             self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1)])
 
 
+BATCH_KEYS = ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")
+
+
+class HostBatchFeeder:
+    """Feeds FusedTrainer.train_step from HOST patch batches (what Dataset.gen_random_patches would produce on a CPU
+    loader, models/dataset_loader.py:223-277) and returns the loss terms to the host, without stalling the GPU:
+      * every batch (8 tensors + the stratified jitter) is packed into ONE pinned staging buffer and moved with ONE
+        cudaMemcpyAsync on a copy stream into one of `depth` device slots, overlapping the previous step's kernels;
+      * the compute stream waits on the slot's event only; the slot is released by an event after the step;
+      * the step's loss terms (stats[8], totals[4]) are copied device->host into a pinned ring every step (async);
+        `losses()` synchronises once and decodes them."""
+
+    def __init__(self, tr: "FusedTrainer", depth: int = 2, log_capacity: int = 4096):
+        self.tr, self.depth = tr, depth
+        n = tr.n_patches
+        shapes = dict(rays_o=(n, 3), rays_d=(n, P, 3), plane_n=(n, 3), near=(n,), far=(n,), v_inv=(n, P, 9), normal_gt=(n, P, 3),
+                      mask=(n, P), jitter=(n,))
+        self.layout, off = {}, 0
+        for k, shp in shapes.items():
+            cnt = int(np.prod(shp))
+            self.layout[k] = (off, cnt, shp)
+            off += (cnt + 3) // 4 * 4          # keep every field 16-byte aligned
+        self.floats = off
+        self.h2d_bytes = off * 4
+        self.d2h_bytes = 12 * 4
+        self.host = [torch.empty(off, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.dev = [torch.empty(off, dtype=torch.float32, device=tr.device) for _ in range(depth)]
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=tr.device)
+        self.log_f = torch.zeros(log_capacity, 8, dtype=torch.float32).pin_memory()
+        self.log_i = torch.zeros(log_capacity, 4, dtype=torch.int32).pin_memory()
+        self.n_fed = self.n_run = 0
+
+    def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {k: flat[o:o + c].view(shp) for k, (o, c, shp) in self.layout.items()}
+
+    def new_host_batch(self) -> torch.Tensor:
+        """A pinned, packed host batch for a loader to fill through `views()` (zero-copy hand-over to submit())."""
+        return torch.empty(self.floats, dtype=torch.float32).pin_memory()
+
+    def views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Named field views (rays_o, rays_d, ..., mask, jitter) of a packed batch buffer."""
+        return self._views(flat)
+
+    def pack(self, batch: Dict[str, torch.Tensor], jitter: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Copy an unpacked host batch into a packed pinned buffer (what a loader does when it cannot fill views() directly)."""
+        out = self.new_host_batch() if out is None else out
+        hv = self._views(out)
+        for k in BATCH_KEYS:
+            hv[k].copy_(batch[k].reshape(hv[k].shape))
+        hv["jitter"].copy_(jitter)
+        return out
+
+    def submit(self, batch, jitter: Optional[torch.Tensor] = None) -> None:
+        """Start the H2D copy of one host batch into the next device slot (returns immediately).  `batch` is a packed
+        pinned buffer from new_host_batch()/pack() -- one cudaMemcpyAsync -- or an unpacked dict (+ jitter), packed here."""
+        slot = self.n_fed % self.depth
+        if self.n_fed >= self.depth:
+            self.free[slot].synchronize()            # the step that used this slot `depth` submissions ago has finished
+        src = batch if torch.is_tensor(batch) else self.pack(batch, jitter, self.host[slot])
+        assert src.is_pinned() and src.numel() == self.floats
+        with torch.cuda.stream(self.copy_stream):
+            self.dev[slot].copy_(src, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.n_fed += 1
+
+    def step(self) -> None:
+        """Run one training iteration on the oldest submitted batch; queue the async read-back of its loss terms."""
+        assert self.n_run < self.n_fed, "submit() a batch first"
+        tr, slot = self.tr, self.n_run % self.depth
+        cur = torch.cuda.current_stream(tr.device)
+        cur.wait_event(self.ready[slot])
+        dv = self._views(self.dev[slot])
+        tr.train_step(batch={k: dv[k] for k in BATCH_KEYS}, jitter=dv["jitter"])
+        i = self.n_run % self.log_f.shape[0]
+        self.log_f[i].copy_(tr.buf.stats, non_blocking=True)
+        self.log_i[i].copy_(tr.buf.totals, non_blocking=True)
+        self.free[slot].record(cur)
+        self.n_run += 1
+
+    def losses(self) -> List[Dict[str, float]]:
+        """Synchronise and decode the logged loss terms of the last min(n_run, log_capacity) steps."""
+        torch.cuda.current_stream(self.tr.device).synchronize()
+        c, tr = self.tr.conf, self.tr
+        out = []
+        cap = self.log_f.shape[0]
+        for i in range(max(0, self.n_run - cap), self.n_run):
+            r, t = self.log_f[i % cap].tolist(), self.log_i[i % cap].tolist()
+            S = max(t[0], 1)
+            normal, mask, eik = r[1] / r[0], r[2] / (tr.n_patches * P), r[3] / (S * P)
+            out.append(dict(loss=c["normal_weight"] * normal + c["mask_weight"] * mask + c["eikonal_weight"] * eik, normal=normal,
+                            mask=mask, eikonal=eik, n_samples=t[0], overflow=t[2]))
+        return out
+
+
 def make_batch_struct(rays_o, rays_d, plane_n, near, far, v_inv, normal_gt, mask) -> SnbPatchBatch:
     """rays_o may be [N,3] or the reference's expanded [N,3,3,3] (only the centre origin is read)."""
     n = rays_d.shape[0]
@@ -376,6 +472,10 @@ class FusedTrainer:
         self.optimizer_step()
         self.iter_step += 1
         self.lr = self.conf["learning_rate"] * self._lr_factor()
+
+    # -- host-fed training (the end-to-end path: batches arrive in HOST memory, losses go back to the host) -----------
+    def host_feeder(self, depth: int = 2, log_capacity: int = 4096) -> "HostBatchFeeder":
+        return HostBatchFeeder(self, depth, log_capacity)
 
     # -- host-side readbacks (sync) ---------------------------------------------------------------
     def loss_terms(self) -> Dict[str, float]:
