@@ -40,15 +40,18 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  The poller is started ahead of
+    the warm-up (nvidia-smi takes a few hundred ms to emit its first row); rows are time-stamped on arrival and only those
+    that fall inside [mark_start(), mark_end()] are summarised."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index=0):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -58,23 +61,35 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
+            time.sleep(0.12)          # let the row that covers the end of the region arrive
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [r for ts, r in self.rows if len(r) >= 9 and self.t0 is not None and self.t0 <= ts <= (self.t1 or ts) + 0.06]
+        where = "timed region"
+        if not ok:   # region shorter than the polling period: take the rows closest to it
+            ok = [r for ts, r in self.rows if len(r) >= 9 and self.t0 is not None and abs(ts - self.t0) < 0.5]
+            where = "within 0.5 s of the timed region"
+        sm = [float(r[1]) for r in ok if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in ok if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        for r in ok:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "window": where}
 
 
 def cpu_port_run(steps, warmup, n_patches=64, threads=None):
@@ -142,6 +157,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=10 ** 9, help="cap on the e2e arm's steps (default: same K)")
+    ap.add_argument("--workload", default="diligent", choices=["diligent", "own_objects"],
+                    help="diligent: BASELINE configs[1] (default, the headline); own_objects: configs[2] (36 views 1512x2016, own_objects.conf schedule)")
     ap.add_argument("--flush-l2", action="store_true", help="time every step separately and overwrite a 512 MB buffer between steps (cold L2)")
     ap.add_argument("--ref-cuda-steps", type=int, default=100, help="steps of the reference-shaped CUDA path timed beside ours at N=1 (0 = skip)")
     args = ap.parse_args()
@@ -164,8 +181,15 @@ def main():
     from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
     from supernormal_b200.trainer import FusedTrainer
 
-    ds = SyntheticDataset(SyntheticScene(), device=dev)
-    tr = FusedTrainer(ds, dict(DILIGENT_CONF), device=dev, seed=0, world_size=world, rank=rank)
+    from supernormal_b200.synthetic import OWN_OBJECTS_CONF
+    if args.workload == "own_objects":
+        # view count / resolution of the authors' own captures are not pinned in the reference repo (data not shipped): SURVEY.md §8d
+        scene, CONF = SyntheticScene(n_views=36, H=1512, W=2016, exclude_views=()), OWN_OBJECTS_CONF
+        workload = "own_objects.conf-shaped training: 36 views 2016x1512 synthetic sphere normals, 2048 patches x 3x3 rays/step, 14-level hash grid T=2^19, 30000-it schedule from random init"
+    else:
+        scene, CONF, workload = SyntheticScene(), DILIGENT_CONF, WORKLOAD
+    ds = SyntheticDataset(scene, device=dev)
+    tr = FusedTrainer(ds, dict(CONF), device=dev, seed=0, world_size=world, rank=rank)
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -173,6 +197,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local).start()
     for _ in range(W):
         tr.train_step()
     # ---- timed region: device-resident sampling ----------------------------------------------
@@ -180,30 +205,32 @@ def main():
     _lib.LAUNCH_COUNT = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     spr = []
-    with ClockSampler(local) as clk:
-        barrier()
-        torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly the timed steps
-        ev0.record()
-        Kr = min(K, args.ref_cuda_steps) if world == 1 else 0
-        evr = torch.cuda.Event(enable_timing=True)
-        flush_ms = 0.0
+    barrier()
+    clk.mark_start()
+    torch.cuda.profiler.start()   # `ncu --profile-from-start off` captures exactly the timed steps
+    ev0.record()
+    Kr = min(K, args.ref_cuda_steps) if (world == 1 and args.workload == "diligent") else 0
+    evr = torch.cuda.Event(enable_timing=True)
+    flush_ms = 0.0
+    if args.flush_l2:
+        junk = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        pairs = []
+    for i in range(K):
         if args.flush_l2:
-            junk = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-            pairs = []
-        for i in range(K):
-            if args.flush_l2:
-                junk.fill_(i & 0xff)
-                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-            tr.train_step()
-            if args.flush_l2:
-                b_.record()
-                pairs.append((a, b_))
-            if i + 1 == Kr:
-                evr.record()   # our time over the same schedule window the reference-shaped path is timed on
-        ev1.record()
-        barrier()
-        torch.cuda.profiler.stop()
+            junk.fill_(i & 0xff)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        tr.train_step()
+        if args.flush_l2:
+            b_.record()
+            pairs.append((a, b_))
+        if i + 1 == Kr:
+            evr.record()   # our time over the same schedule window the reference-shaped path is timed on
+    ev1.record()
+    barrier()
+    clk.mark_end()
+    torch.cuda.profiler.stop()
+    clk.stop()
     ms = ev0.elapsed_time(ev1)
     if args.flush_l2:
         ms = sum(a.elapsed_time(b_) for a, b_ in pairs)   # steps only; the flush writes between them are not counted
@@ -223,7 +250,7 @@ def main():
     Ke = min(args.e2e_steps, K)
     pool = [{k: v.cpu() for k, v in tr.sample_batch().items()} for _ in range(16)]     # HOST batches (a CPU loader's output)
     jit_pool = [torch.rand(tr.n_patches) for _ in range(16)]
-    te = FusedTrainer(ds, dict(DILIGENT_CONF), device=dev, seed=0, world_size=world, rank=rank)
+    te = FusedTrainer(ds, dict(CONF), device=dev, seed=0, world_size=world, rank=rank)
     for _ in range(W):
         te.train_step()
     feeder = te.host_feeder(depth=3, log_capacity=max(Ke, 1))
@@ -251,7 +278,7 @@ def main():
         peak, which = peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "patches_per_gpu": tr.n_patches, "parallelism": f"dp{world}",
+                "config": {"workload": workload, "patches_per_gpu": tr.n_patches, "parallelism": f"dp{world}",
                            "l2_policy": ("flushed: 512 MB overwritten between steps, every step timed separately with CUDA events" if args.flush_l2 else
                                          "not flushed: a training run is a dependent chain of steps -- parameters are rewritten and patches are new random draws every step, "
                                          "so no step repeats an input; the fp16 hash table (<= 24 MB) staying L2-resident across steps is part of the design (--flush-l2 times the cold-L2 case)"),
