@@ -203,6 +203,10 @@ int32_t snb_march_visible(const snb_patch_batch *h_batch, const snb_net *h_net, 
 int32_t snb_compact_samples(int32_t n_patches, const snb_samples *h_samples, snb_stream_t stream);
 /* SDF at arbitrary points, no grad.  mode 0: sdf, 1: sigmoid(-80*sdf) (models/renderer.py:56-60), 2: -sdf */
 int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *h_net, int32_t mode, float *out, snb_stream_t stream);
+/* self-test of the tcgen05 / TMEM plumbing the fused kernels build on: D[128,N] = A[128,K] * B[N,K]^T, kind::tf32 (operands are
+ * rounded to TF32 by the tensor core), fp32 accumulate.  K % 8 == 0, K <= 128, N in {32, 64}.  err (device i32) is set to 1 if the
+ * MMA never signalled completion. */
+int32_t snb_umma_selftest(const float *A, const float *B, float *D, int32_t K, int32_t N, int32_t *err, snb_stream_t stream);
 /* SDF and its analytic gradient d sdf / d x in ONE pass (forward-mode through encode + MLP on the tensor cores):
  * what SDFNetwork.gradient (models/fields.py:107-119) returns for `ad` normals (models/renderer.py:225-226, :345),
  * without the autograd double pass.  sdf: f32[n] or null; grad: f32[n,3]. */
