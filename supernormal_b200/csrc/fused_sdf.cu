@@ -5,6 +5,7 @@
 //   sdf_bwd_patch   MLP backward (recomputing layer 0 from the kept features), weight gradients as a
 //                   shared-memory-tiled contraction, hash-table scatter with vector fp32 atomics
 #include "sdf_mma.cuh"
+#include "umma.cuh"
 
 namespace snb {
 
@@ -303,6 +304,302 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
     if (lane == 0) atomicAdd(net_grad + kOffB1, accB1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward with tcgen05 (5th-gen tensor cores, TMEM accumulators)
+// ---------------------------------------------------------------------------------------------
+// CTA = 128 threads = one tile of 128 points; thread t owns point t, and TMEM lane t is row t of every accumulator, so
+// tcgen05.ld hands each thread exactly its point's 64 pre-activations / 32 feature gradients (no layout shuffling).
+//   (1) Z[128 x 64]  = X1[128 x 40] * B1^T        tcgen05.mma kind::tf32, 5 k-steps x (hi, lo) weights
+//         X1 = [ fp16 features (exact in TF32) | x_hi | x_lo | 1 | 0 ],   B1 = [ W0feat | W0xyz | W0xyz | b0 | 0 ] split hi + lo:
+//         products exact to 2^-22 (the recomputed z feeds sigmoid(100 z), it must match the forward)
+//   (2) dz = dsdf * W1 * sigmoid(100 z) per thread -> TF32-rounded into a K-major tile;   dW1 / db1 by warp reductions
+//   (3) U[128 x 32]  = dz[128 x 64] * W0feat (hi)  tcgen05.mma, 8 k-steps  -> d loss / d features, scattered per thread
+//         (single TF32 pass: 2^-11 relative, the precision class of tiny-cuda-nn's fp16 gradient path)
+//   (4) dW0T[40 x 64] += X1^T dz                     warp-level mma.sync m16n8k8 on the same two tiles (contraction over the
+//         points; tcgen05 cannot take MN-major TF32 operands without the 128B_BASE32B swizzle), persistent accumulators.
+//         dz enters as the TF32 tile (rounded to nearest: unbiased, 2^-12 rms per element, averaged over the points); a bf16
+//         side tile for the residual was measured (+14 % kernel time for errors far below the minibatch noise) and dropped.
+// (3) runs on the tensor pipe while the warps do (4).
+constexpr int kK1 = 40;                      // columns of X1: 32 feature slots | x_hi (3) | x_lo (3) | 1 | pad
+constexpr int kColXhi = 32, kColXlo = 35, kColOne = 38;
+constexpr uint32_t kBwdTmemCols = 128;       // Z: columns 0..63, U: 64..95
+constexpr size_t kBwdUmmaSmem = umma::tile_bytes(64, kK1) * 2 + umma::tile_bytes(32, 64) + umma::tile_bytes(128, kK1) + umma::tile_bytes(128, 64);
+
+__global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
+                                                                    const __half2 *__restrict__ feats,
+                                                                    const float *__restrict__ d_sdf0,
+                                                                    const float *__restrict__ d_sdf1,
+                                                                    float *__restrict__ table_grad, float *__restrict__ net_grad,
+                                                                    int *__restrict__ err_flag) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_z, bar_u;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_w1[kH];
+    __shared__ LevelCtx s_lvl[SNB_MAX_LEVELS];
+    uint8_t *b1hi = smem_raw, *b1lo = b1hi + umma::tile_bytes(64, kK1), *b2 = b1lo + umma::tile_bytes(64, kK1);
+    uint8_t *a1 = b2 + umma::tile_bytes(32, 64), *a2 = a1 + umma::tile_bytes(128, kK1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t L = net.meta.n_levels, n_active = net.n_active;
+
+    // ---- one-time staging: weights (TF32 hi / lo), level table, TMEM, barriers
+    {
+        const float *W = net.net;
+        for (int e = tid; e < 64 * kK1; e += 128) {
+            const int h = e / kK1, k = e % kK1;
+            float w = 0.f;
+            bool lo_zero = false;
+            if (k < 32) w = __ldg(W + kOffW0T + (3 + k) * kH + h);
+            else if (k < kColXlo) w = __ldg(W + kOffW0T + (k - kColXhi) * kH + h);
+            else if (k < kColOne) { w = __ldg(W + kOffW0T + (k - kColXlo) * kH + h); lo_zero = true; }   // x_lo * W_lo is below 2^-22
+            else if (k == kColOne) w = __ldg(W + kOffB0 + h);
+            const float hi = __uint_as_float(to_tf32(w));
+            *reinterpret_cast<float *>(b1hi + umma::kmajor_off(h, k, kK1)) = hi;
+            *reinterpret_cast<float *>(b1lo + umma::kmajor_off(h, k, kK1)) = lo_zero ? 0.f : __uint_as_float(to_tf32(w - hi));
+        }
+        for (int e = tid; e < 32 * 64; e += 128) {
+            const int j = e / 64, h = e % 64;
+            *reinterpret_cast<float *>(b2 + umma::kmajor_off(j, h, 64)) = __uint_as_float(to_tf32(__ldg(W + kOffW0T + (3 + j) * kH + h)));
+        }
+        if (tid < kH) s_w1[tid] = __ldg(W + kOffW1 + tid);
+        if (tid < SNB_MAX_LEVELS) s_lvl[tid] = lt.lv[tid];
+        if (warp == 0) umma::tmem_alloc(&s_tmem, kBwdTmemCols);
+        if (tid == 0) { umma::mbar_init(&bar_z, 1); umma::mbar_init(&bar_u, 1); }
+        umma::fence_smem_to_async_proxy();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    }
+    const uint32_t tmem = s_tmem;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(32 * warp) << 16);
+    const uint32_t a1_addr = umma::smem_u32(a1), a2_addr = umma::smem_u32(a2);
+    const uint32_t b1hi_addr = umma::smem_u32(b1hi), b1lo_addr = umma::smem_u32(b1lo), b2_addr = umma::smem_u32(b2);
+    const uint32_t idesc_z = umma::idesc_tf32(128, 64), idesc_u = umma::idesc_tf32(128, 32);
+
+    const int S = sm.totals[0], E = sm.totals[1];
+    const int64_t Q = (int64_t)S + E;                            // sample starts + own interval ends; point p = 9 q + k
+    // Tile = kTileQ consecutive q x 9 rays, RAY-major over the threads: thread t -> ray k = t / kTileQ, q = q0 + t % kTileQ, so that
+    // consecutive lanes walk ALONG a ray (spacing = the marching step, far below the cell size of most levels) and the
+    // segmented reduction of the scatter below finds long runs of lanes in the same grid cell.
+    constexpr int kTileQ = 14;
+    const int tk = tid / kTileQ, tj = tid % kTileQ;
+    const int n_feat_steps = (int)(2 * n_active + 7) >> 3;     // feature k-steps of (1) that can be non-zero
+    // (4): output tiles [3 m-tiles (input columns 0..15, 16..31, 32..47) x 8 n-tiles (hidden)] dealt to the 4 warps
+    const int n_mt = (2 * (int)n_active > 16) ? 3 : 2;          // m-tile 1 (features 16..31) only when > 8 levels are active
+    float wacc[6][4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wacc[i][c] = 0.f;
+    float accW1a = 0.f, accW1b = 0.f, accB1 = 0.f;
+    uint32_t phase = 0;
+    bool failed = false;
+
+    for (int64_t q0 = (int64_t)blockIdx.x * kTileQ; q0 < Q; q0 += (int64_t)gridDim.x * kTileQ) {
+        // ---- stage this thread's point: row tid of X1
+        const int64_t p = (q0 + tj) * SNB_PATCH + tk;
+        const bool valid = tk < SNB_PATCH && q0 + tj < Q;
+        float dsdf = 0.f;
+        PointRef r;
+        r.px = r.py = r.pz = 0.f;
+        if (valid) {
+            r = decode_point(p, S, b, sm);
+            if (!r.is_end) {
+                dsdf = __ldg(d_sdf0 + (int64_t)r.s * SNB_PATCH + r.k);
+                // this start also served as the previous interval's end when that interval had no own end query
+                if (r.s > 0 && __ldg(sm.end_slot + r.s - 1) < 0) dsdf += __ldg(d_sdf1 + (int64_t)(r.s - 1) * SNB_PATCH + r.k);
+            } else {
+                dsdf = __ldg(d_sdf1 + (int64_t)r.s * SNB_PATCH + r.k);
+            }
+        }
+        {
+            const __half2 *fr = feats + p * L;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {       // 8 chunks of 4 feature columns (2 levels each)
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && 2 * q < (int)n_active) {
+                    float2 f0 = __half22float2(fr[2 * q]);
+                    v.x = f0.x; v.y = f0.y;
+                    if (2 * q + 1 < (int)n_active) {
+                        float2 f1 = __half22float2(fr[2 * q + 1]);
+                        v.z = f1.x; v.w = f1.y;
+                    }
+                }
+                *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 4 * q, kK1)) = v;
+            }
+            const float xh = __uint_as_float(to_tf32(r.px)), yh = __uint_as_float(to_tf32(r.py)), zh = __uint_as_float(to_tf32(r.pz));
+            const float xl = __uint_as_float(to_tf32(r.px - xh)), yl = __uint_as_float(to_tf32(r.py - yh)), zl = __uint_as_float(to_tf32(r.pz - zh));
+            *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 32, kK1)) = make_float4(xh, yh, zh, xl);
+            *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 36, kK1)) = make_float4(yl, zl, 1.f, 0.f);
+        }
+        umma::fence_smem_to_async_proxy();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+
+        // ---- (1) Z = X1 B1^T
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int s = 0; s < kK1 / 8; ++s) {
+                if (s < 4 && s >= n_feat_steps) continue;      // all-zero feature columns
+                const uint64_t ad = umma::kmajor_desc(a1_addr + 256u * s, kK1);
+                umma::mma_tf32(tmem, ad, umma::kmajor_desc(b1hi_addr + 256u * s, kK1), idesc_z, acc);
+                umma::mma_tf32(tmem, ad, umma::kmajor_desc(b1lo_addr + 256u * s, kK1), idesc_z, 1);
+                acc = 1;
+            }
+            umma::commit(&bar_z);
+        }
+        if (!umma::mbar_wait(&bar_z, phase)) failed = true;
+        umma::fence_after_sync();
+
+        // ---- (2) dz, dW1 / db1
+        {
+            float hact[kH];
+#pragma unroll
+            for (int c0 = 0; c0 < kH; c0 += 16) {
+                float z[16];
+                umma::tmem_ld16(tmem_lane + (uint32_t)c0, z);
+                umma::tmem_ld_wait();
+                float dzv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float sp, sg;
+                    softplus100_both(z[i], sp, sg);
+                    hact[c0 + i] = dsdf * sp;
+                    dzv[i] = __uint_as_float(to_tf32(dsdf * s_w1[c0 + i] * sg));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4 *>(a2 + umma::kmajor_off(tid, c0 + 4 * q, 64)) = make_float4(dzv[4 * q], dzv[4 * q + 1], dzv[4 * q + 2], dzv[4 * q + 3]);
+
+            }
+            warp_transpose_reduce64(hact, lane);
+            accW1a += hact[0];
+            accW1b += hact[1];
+            float ds = dsdf;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            accB1 += ds;
+        }
+        umma::fence_smem_to_async_proxy();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+
+        // ---- (3) U = dz W0feat  (async on the tensor pipe)
+        if (tid == 0 && n_active > 0) {
+            for (int s = 0; s < 8; ++s)
+                umma::mma_tf32(tmem + 64u, umma::kmajor_desc(a2_addr + 256u * s, 64), umma::kmajor_desc(b2_addr + 256u * s, 64), idesc_u, s > 0);
+            umma::commit(&bar_u);
+        }
+
+        // ---- (4) dW0T[col][h] += sum_p X1[p][col] dz[p][h]   (mma.sync; A = X1^T, B = dz read from the K-major tiles)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int tile = warp + 4 * i;                      // 24 tiles: mt = tile / 8, nt = tile % 8
+            const int mt = tile >> 3, nt = tile & 7;
+            if (mt == 1 && n_mt < 3) continue;                  // features 16..31 inactive
+            if (mt == 0 && n_active == 0) continue;
+            for (int ks = 0; ks < 16; ++ks) {
+                const int pa = 8 * ks + t;                      // points (k index): pa, pa + 4
+                const int ca = 16 * mt + g;                     // columns (m index): ca, ca + 8
+                uint32_t a[4];
+                a[0] = *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa, ca, kK1));
+                a[1] = (ca + 8 < kK1) ? *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa, ca + 8, kK1)) : 0u;
+                a[2] = *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa + 4, ca, kK1));
+                a[3] = (ca + 8 < kK1) ? *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa + 4, ca + 8, kK1)) : 0u;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(a2 + umma::kmajor_off(pa, 8 * nt + g, 64));
+                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(a2 + umma::kmajor_off(pa + 4, 8 * nt + g, 64));
+                mma_tf32(wacc[i], a, b0, b1);
+            }
+        }
+
+        // ---- scatter d loss / d features (thread-per-point, straight from TMEM)
+        if (n_active > 0) {
+            if (!umma::mbar_wait(&bar_u, phase)) failed = true;
+            umma::fence_after_sync();
+            // The table scatter is bound by the L2 atomic units (~64 red.v2.f32 lanes per clock chip-wide: 67 M of them are the whole
+            // 530 us of the FMA kernel at 14 levels), so contributions to the same grid cell are summed in the warp first:
+            // segmented inclusive scan over runs of consecutive lanes with the same cell (16 values: 8 corners x 2 features),
+            // the last lane of each run issues the run's 8 atomics.  Levels too fine to form runs take the direct path.
+            const bool live = valid && dsdf != 0.f;
+#pragma unroll 1
+            for (uint32_t l = 0; l < n_active; ++l) {
+                float g0, g1;
+                umma::tmem_ld2(tmem_lane + 64u + 2u * l, g0, g1);    // warp-collective: every lane takes part
+                umma::tmem_ld_wait();
+                const LevelCtx c = s_lvl[l];
+                const Cell cell = cell_of(c, r.px, r.py, r.pz);
+                const unsigned long long key = live ? (((unsigned long long)(cell.g[0] & 0x1FFFFFu)) | ((unsigned long long)(cell.g[1] & 0x1FFFFFu) << 21) |
+                                                       ((unsigned long long)(cell.g[2] & 0x1FFFFFu) << 42))
+                                                    : ~0ull;
+                const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+                float2 *gt = reinterpret_cast<float2 *>(table_grad) + c.offset;
+                if (__popc(heads) > 20) {                             // (almost) no two neighbours share a cell
+                    if (live) {
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; ++k) {
+                            float w = corner_weight(cell, k);
+                            atomicAdd(gt + corner_index(c, cell, k), make_float2(w * g0, w * g1));
+                        }
+                    }
+                    continue;
+                }
+                const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+                float vx[8], vy[8];
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const float w = live ? corner_weight(cell, k) : 0.f;
+                    vx[k] = w * g0;
+                    vy[k] = w * g1;
+                }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const bool take = lane - d >= run_start;
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        const float ux = __shfl_up_sync(0xffffffffu, vx[k], d), uy = __shfl_up_sync(0xffffffffu, vy[k], d);
+                        if (take) { vx[k] += ux; vy[k] += uy; }
+                    }
+                }
+                if (tail && live) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) atomicAdd(gt + corner_index(c, cell, k), make_float2(vx[k], vy[k]));
+                }
+            }
+        }
+        phase ^= 1u;
+        umma::fence_before_sync();
+        __syncthreads();          // tiles a1 / a2 and both accumulators are free again
+        umma::fence_after_sync();
+    }
+
+    // ---- flush
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int tile = warp + 4 * i, mt = tile >> 3, nt = tile & 7;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = 16 * mt + g + 8 * (c >> 1), h = 8 * nt + 2 * t + (c & 1);
+            float *dst = nullptr;
+            if (col < 32) { if (col < 2 * (int)n_active) dst = net_grad + kOffW0T + (3 + col) * kH + h; }
+            else if (col < kColXlo) dst = net_grad + kOffW0T + (col - kColXhi) * kH + h;
+            else if (col < kColOne) dst = net_grad + kOffW0T + (col - kColXlo) * kH + h;
+            else if (col == kColOne) dst = net_grad + kOffB0 + h;
+            if (dst && wacc[i][c] != 0.f) atomicAdd(dst, wacc[i][c]);
+        }
+    }
+    atomicAdd(net_grad + kOffW1 + 2 * lane, accW1a);
+    atomicAdd(net_grad + kOffW1 + 2 * lane + 1, accW1b);
+    if (lane == 0) atomicAdd(net_grad + kOffB1, accB1);
+    if (failed && tid == 0 && err_flag) atomicExch(err_flag, 1);
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kBwdTmemCols);
+}
+
 static int32_t check_net(const snb_net *net, const char *who) {
     SNB_REQUIRE(net, SNB_ERR_NULL, "%s: null net", who);
     SNB_REQUIRE(net->table_f16 && net->net, SNB_ERR_NULL, "%s: null table/net", who);
@@ -387,12 +684,21 @@ extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *ne
     SNB_REQUIRE(feats && d_sdf0 && d_sdf1 && table_grad && net_grad, SNB_ERR_NULL, "sdf_bwd_patch: null buffer");
     SNB_REQUIRE(aligned(table_grad, 8), SNB_ERR_ALIGN, "sdf_bwd_patch: table_grad must be 8-byte aligned");
     static const size_t smem = sizeof(float) * (kNetFloats + kTile * kDzStride + kTile * kXStride);
+    // tcgen05 kernel from 3 active levels on (measured: 104 vs 113 us at 4 levels, 432 vs 532 us at 14; the FMA kernel is ahead at
+    // 1-2 levels, where neither GEMMs nor atomics dominate).  SNB_BWD_UMMA=0 / 1 forces one of them (cross-checks).
+    static const int force_umma = getenv("SNB_BWD_UMMA") ? atoi(getenv("SNB_BWD_UMMA")) : -1;
+    const int use_umma = force_umma >= 0 ? force_umma : (net->n_active >= 3);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(sdf_bwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(sdf_bwd_patch_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
         configured = true;
     }
-    sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
+    if (use_umma)
+        sdf_bwd_patch_umma_kernel<<<kNumSMs * 2, 128, kBwdUmmaSmem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1,
+                                                                                    table_grad, net_grad, sm->totals + 2);
+    else
+        sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
     SNB_LAUNCH_CHECK("sdf_bwd_patch");
     return SNB_OK;
 }

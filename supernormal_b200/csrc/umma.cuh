@@ -33,10 +33,14 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_byte_addr, int K) 
     return d;
 }
 
+// MN-major TF32 operands are NOT available in this layout: tcgen05 accepts them only with the 128B_BASE32B swizzle (measured:
+// wrong results with a no-swizzle MN-major descriptor), and for M = 128 the N extent must be a multiple of 16.  Contractions over
+// the row index of these tiles therefore go through warp-level mma.sync (fused_sdf.cu, step (4) of the backward).
 // instruction descriptor, kind::tf32, fp32 accumulate, both operands K-major:
 // c_format = F32 (1) [4,6) | a_format = TF32 (2) [7,10) | b_format = TF32 (2) [10,13) | N >> 3 [17,23) | M >> 4 [24,29)
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// a_major [15] / b_major [16]: 0 = K-major, 1 = MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- TMEM allocation (one warp, all lanes) ---------------------------------------------------------------------------
@@ -88,6 +92,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
                  : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float &v0, float &v1) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    v0 = __uint_as_float(r0);
+    v1 = __uint_as_float(r1);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

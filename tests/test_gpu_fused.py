@@ -124,9 +124,10 @@ def test_sdf_eval_grad_argument_errors(cuda):
     assert l.snb_sdf_eval_grad(0, None, C.byref(net), None, None, None) == 0     # empty input is a no-op
 
 
-@pytest.mark.parametrize("variance,cut_active", [(0.3, False), (0.75, True)])
-def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active):
-    ds, osdf, odev, orend, tr, batch_cpu = _setup(cuda, variance=variance)
+@pytest.mark.parametrize("variance,cut_active,n_active", [(0.3, False, 4), (0.75, True, 4), (0.3, False, 2), (0.3, False, 6)])
+def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active):
+    """n_active >= 3 runs the tcgen05 backward, n_active < 3 the FMA backward (fused_sdf.cu: snb_sdf_bwd_patch)."""
+    ds, osdf, odev, orend, tr, batch_cpu = _setup(cuda, variance=variance, n_active=n_active)
     o, d, pn, vinv, nrm, msk = batch_cpu
     batch, near, far = _to_gpu_batch(ds, batch_cpu, cuda)
     step = 0.02
@@ -221,10 +222,13 @@ def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active):
     tr.buf.stats[4] = 0.0
     call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(tr.buf.stats), ptr(m.grad))
     got = flat_grads()
-    for k in ("table", "g0", "v0", "b0", "g1", "v1"):
+    # The tcgen05 backward (>= 3 active levels) forms d loss/d features (-> table) and dW0 / db0 from dz rounded to TF32 (round to
+    # nearest: unbiased, 2^-12 rms relative per element -- the precision class of the fp16 dL/dy tiny-cuda-nn's own backward
+    # consumes); sums over 64 hidden units / many points average that down.  z recompute, dW1, db1 are fp32-accurate.
+    for k, tol, tol_max in (("table", 6e-4, 2e-3), ("g0", 5e-4, 1e-3), ("v0", 5e-4, 1e-3), ("b0", 5e-4, 1e-3), ("g1", 2e-4, 5e-4), ("v1", 2e-4, 5e-4)):
         relk = (got[k] - ref[k]).norm().item() / max(ref[k].norm().item(), 1e-12)
-        assert relk <= 2e-4, (k, relk)
-        assert (got[k] - ref[k]).abs().max().item() <= 5e-4 * max(ref[k].abs().max().item(), 1e-8), k
+        assert relk <= tol, (k, relk)
+        assert (got[k] - ref[k]).abs().max().item() <= tol_max * max(ref[k].abs().max().item(), 1e-8), k
 
 
 def orend_full_count(orend, o, d, near, far, jitter, step):
