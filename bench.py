@@ -290,8 +290,17 @@ def main():
                 "kernels": prof}
         if prof.get("dominant"):
             dk = prof["dominant"]
+            traffic, traffic_note = None, None
+            tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # dram__bytes_read+write per launch from one `ncu --set full` capture
+            if os.path.exists(tp):
+                tj = json.load(open(tp))
+                if tj.get("entry_point") == dk["name"]:
+                    traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
             line["roofline"] = {"bound": "hbm", "kernel": dk["name"], "achieved": dk["gbs"], "peak": peak, "unit": "GB/s", "frac": dk["gbs"] / peak,
-                                "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": dk["bytes"], "avg_us": dk["us"]}
+                                "traffic": traffic, "traffic_note": traffic_note, "peak_source": which, "algorithmic_bytes_per_launch": dk["bytes"],
+                                "avg_us": dk["us"],
+                                "note": "the step's kernels are latency / issue / L2-atomic bound at 2048 patches per GPU (DESIGN.md section 5); the only HBM-streaming "
+                                        "kernel is the Adam sweep (snb_train_optim in kernels.hbm_model)"}
         if Kr > 0:
             ours_ms = ev0.elapsed_time(evr) / Kr
             for backend, key in (("reference", "reference_cuda_path"), ("dropin", "dropin_api_path")):

@@ -497,14 +497,23 @@ class FusedTrainer:
         na = m.n_active
         if name == "snb_sdf_fwd_patch":      # write sdf (4 B) + kept features (4 B/level); read packed samples (12 B each)
             return M * (4 + 4 * na) + S * 12
-        if name == "snb_sdf_bwd_patch":      # read features + seeds; table-gradient read-modify-write 8 corners x 8 B per level
-            return M * (4 * na + 4) + 2 * P * S * 4 + M * na * 8 * 8 * 2
+        if name == "snb_sdf_bwd_patch":      # read kept features (4 B/level) + positions' inputs + seeds (d_sdf0, d_sdf1); the table-gradient
+            return M * (4 * na + 4) + 2 * P * S * 4   # reductions are L2 traffic (l2_bytes), SURVEY.md §8d
         if name == "snb_train_optim":         # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
             return (SMALL_PAD + 2 * m.offsets[na]) * (16 + 16) + 2 * m.offsets[na] * 2
         if name == "snb_march_visible":      # 40 B in per ray + 8 B per emitted sample (scratch)
             return self.n_patches * 40 + S * 8
         if name == "snb_render_fused":       # sdf read + d_sdf0/d_sdf1 written per point, packed samples, per-ray constants and outputs
             return P * S * 16 + P * E * 4 + S * 12 + self.n_patches * P * (36 + 12 + 12 + 4 + 16)
+        return None
+
+    def l2_bytes(self, name: str, S: int, E: int) -> Optional[int]:
+        """Useful L2 gather / reduction bytes of one launch (L * 8 corners * 4 B per point gathered, 8 B per corner reduced)."""
+        M, na = P * (S + E), self.model.n_active
+        if name == "snb_sdf_fwd_patch":
+            return M * na * 8 * 4
+        if name == "snb_sdf_bwd_patch":
+            return M * na * 8 * 8
         return None
 
     def profile_kernels(self, steps: int = 20) -> dict:
@@ -532,12 +541,18 @@ class FusedTrainer:
                "sum_us_per_step": round(total, 2), "avg_samples": S_acc / steps, "avg_ends": E_acc / steps,
                "n_active": self.model.n_active}
         S, E = int(S_acc / steps), int(E_acc / steps)
+        out["hbm_model"] = {}
         for name in sorted(per_step, key=lambda k: -per_step[k]):
             nb = self.algorithmic_bytes(name, S, E)
             if nb:
                 us = sum(agg[name]) / len(agg[name])
                 calls = len(agg[name]) / steps
-                out["dominant"] = {"name": name, "us": us, "bytes": nb, "gbs": nb / (us * 1e-6) / 1e9, "share": per_step[name] / total,
-                                   "launches_per_step": calls}
-                break
+                rec = {"name": name, "us": us, "bytes": nb, "gbs": nb / (us * 1e-6) / 1e9, "share": per_step[name] / total,
+                       "launches_per_step": calls}
+                out["hbm_model"][name] = {"us": round(us, 2), "algorithmic_bytes": nb, "gbs": round(rec["gbs"], 1)}
+                l2 = self.l2_bytes(name, S, E)
+                if l2:
+                    out["hbm_model"][name].update(l2_useful_bytes=l2, l2_useful_gbs=round(l2 / (us * 1e-6) / 1e9, 1))
+                if "dominant" not in out:
+                    out["dominant"] = rec
         return out
