@@ -494,23 +494,34 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
         }
 
         // ---- (4) dW0T[col][h] += sum_p X1[p][col] dz[p][h]   (mma.sync; A = X1^T, B = dz read from the K-major tiles)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int tile = warp + 4 * i;                      // 24 tiles: mt = tile / 8, nt = tile % 8
-            const int mt = tile >> 3, nt = tile & 7;
-            if (mt == 1 && n_mt < 3) continue;                  // features 16..31 inactive
-            if (mt == 0 && n_active == 0) continue;
+        // warp owns the hidden tiles nt = warp, warp + 4 and all three column tiles: wacc[2 mt + j].  Fragment addresses in the
+        // core-matrix layout: point 8 ks + t (+4) -> ks * (K/4) * 128 + t * 16 (+64); column c -> (c / 4) * 128 + (c % 4) * 4.
+        {
+            const uint8_t *ab = a1 + (g >> 2) * 128 + (g & 3) * 4 + t * 16;              // column g of m-tile 0; m-tile mt: + mt * 512
+            const uint8_t *bb0 = a2 + (2 * warp + (g >> 2)) * 128 + (g & 3) * 4 + t * 16;  // hidden 8 warp + g; second tile: + 8 * 128
+            const bool m0 = n_active > 0, m1 = n_mt == 3;
+#pragma unroll 2
             for (int ks = 0; ks < 16; ++ks) {
-                const int pa = 8 * ks + t;                      // points (k index): pa, pa + 4
-                const int ca = 16 * mt + g;                     // columns (m index): ca, ca + 8
+                const uint8_t *ak = ab + ks * (kK1 / 4) * 128, *bk = bb0 + ks * (64 / 4) * 128;
+                const uint32_t b00 = *reinterpret_cast<const uint32_t *>(bk), b01 = *reinterpret_cast<const uint32_t *>(bk + 64);
+                const uint32_t b10 = *reinterpret_cast<const uint32_t *>(bk + 1024), b11 = *reinterpret_cast<const uint32_t *>(bk + 1024 + 64);
                 uint32_t a[4];
-                a[0] = *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa, ca, kK1));
-                a[1] = (ca + 8 < kK1) ? *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa, ca + 8, kK1)) : 0u;
-                a[2] = *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa + 4, ca, kK1));
-                a[3] = (ca + 8 < kK1) ? *reinterpret_cast<const uint32_t *>(a1 + umma::kmajor_off(pa + 4, ca + 8, kK1)) : 0u;
-                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(a2 + umma::kmajor_off(pa, 8 * nt + g, 64));
-                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(a2 + umma::kmajor_off(pa + 4, 8 * nt + g, 64));
-                mma_tf32(wacc[i], a, b0, b1);
+                if (m0) {
+                    a[0] = *reinterpret_cast<const uint32_t *>(ak); a[1] = *reinterpret_cast<const uint32_t *>(ak + 256);
+                    a[2] = *reinterpret_cast<const uint32_t *>(ak + 64); a[3] = *reinterpret_cast<const uint32_t *>(ak + 256 + 64);
+                    mma_tf32(wacc[0], a, b00, b01);
+                    mma_tf32(wacc[1], a, b10, b11);
+                }
+                if (m1) {
+                    a[0] = *reinterpret_cast<const uint32_t *>(ak + 512); a[1] = *reinterpret_cast<const uint32_t *>(ak + 512 + 256);
+                    a[2] = *reinterpret_cast<const uint32_t *>(ak + 512 + 64); a[3] = *reinterpret_cast<const uint32_t *>(ak + 512 + 256 + 64);
+                    mma_tf32(wacc[2], a, b00, b01);
+                    mma_tf32(wacc[3], a, b10, b11);
+                }
+                a[0] = *reinterpret_cast<const uint32_t *>(ak + 1024); a[1] = 0u;       // columns 32..39; 40..47 do not exist
+                a[2] = *reinterpret_cast<const uint32_t *>(ak + 1024 + 64); a[3] = 0u;
+                mma_tf32(wacc[4], a, b00, b01);
+                mma_tf32(wacc[5], a, b10, b11);
             }
         }
 
@@ -555,8 +566,11 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
                     vx[k] = w * g0;
                     vy[k] = w * g1;
                 }
+                // a run longer than 16 lanes needs the last doubling step: some lane >= 16 whose run starts at or before lane - 16
+                const bool long_run = __any_sync(0xffffffffu, lane - 16 >= run_start);
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
+                    if (d == 16 && !long_run) break;
                     const bool take = lane - d >= run_start;
 #pragma unroll
                     for (uint32_t k = 0; k < 8; ++k) {
@@ -579,7 +593,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
     // ---- flush
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const int tile = warp + 4 * i, mt = tile >> 3, nt = tile & 7;
+        const int mt = i >> 1, nt = warp + 4 * (i & 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int col = 16 * mt + g + 8 * (c >> 1), h = 8 * nt + 2 * t + (c & 1);
