@@ -395,43 +395,57 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
     uint32_t phase = 0;
     bool failed = false;
 
-    for (int64_t q0 = (int64_t)blockIdx.x * kTileQ; q0 < Q; q0 += (int64_t)gridDim.x * kTileQ) {
-        // ---- stage this thread's point: row tid of X1
+    // Point data of a tile (decode chain: sample -> patch -> rays, seeds, kept features) is fetched one tile AHEAD into registers,
+    // so its dependent global loads overlap the previous tile's MMAs / scatter instead of heading every tile.
+    struct TileRegs {
+        bool valid;
+        float dsdf, px, py, pz;
+        __half2 f[SNB_MAX_LEVELS];
+    };
+    auto fetch = [&](int64_t q0, TileRegs &o) {
         const int64_t p = (q0 + tj) * SNB_PATCH + tk;
-        const bool valid = tk < SNB_PATCH && q0 + tj < Q;
-        float dsdf = 0.f;
-        PointRef r;
-        r.px = r.py = r.pz = 0.f;
-        if (valid) {
-            r = decode_point(p, S, b, sm);
+        o.valid = tk < SNB_PATCH && q0 + tj < Q;
+        o.dsdf = 0.f;
+        o.px = o.py = o.pz = 0.f;
+#pragma unroll
+        for (int l = 0; l < SNB_MAX_LEVELS; ++l) o.f[l] = __float2half2_rn(0.f);
+        if (o.valid) {
+            const PointRef r = decode_point(p, S, b, sm);
+            o.px = r.px; o.py = r.py; o.pz = r.pz;
             if (!r.is_end) {
-                dsdf = __ldg(d_sdf0 + (int64_t)r.s * SNB_PATCH + r.k);
+                o.dsdf = __ldg(d_sdf0 + (int64_t)r.s * SNB_PATCH + r.k);
                 // this start also served as the previous interval's end when that interval had no own end query
-                if (r.s > 0 && __ldg(sm.end_slot + r.s - 1) < 0) dsdf += __ldg(d_sdf1 + (int64_t)(r.s - 1) * SNB_PATCH + r.k);
+                if (r.s > 0 && __ldg(sm.end_slot + r.s - 1) < 0) o.dsdf += __ldg(d_sdf1 + (int64_t)(r.s - 1) * SNB_PATCH + r.k);
             } else {
-                dsdf = __ldg(d_sdf1 + (int64_t)r.s * SNB_PATCH + r.k);
+                o.dsdf = __ldg(d_sdf1 + (int64_t)r.s * SNB_PATCH + r.k);
             }
-        }
-        {
             const __half2 *fr = feats + p * L;
 #pragma unroll
+            for (int l = 0; l < SNB_MAX_LEVELS; ++l)
+                if (l < (int)n_active) o.f[l] = fr[l];
+        }
+    };
+    TileRegs nxt;
+    fetch((int64_t)blockIdx.x * kTileQ, nxt);
+
+    for (int64_t q0 = (int64_t)blockIdx.x * kTileQ; q0 < Q; q0 += (int64_t)gridDim.x * kTileQ) {
+        // ---- stage this thread's point: row tid of X1
+        const bool valid = nxt.valid;
+        const float dsdf = nxt.dsdf;
+        PointRef r;
+        r.px = nxt.px; r.py = nxt.py; r.pz = nxt.pz;
+        {
+#pragma unroll
             for (int q = 0; q < 8; ++q) {       // 8 chunks of 4 feature columns (2 levels each)
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid && 2 * q < (int)n_active) {
-                    float2 f0 = __half22float2(fr[2 * q]);
-                    v.x = f0.x; v.y = f0.y;
-                    if (2 * q + 1 < (int)n_active) {
-                        float2 f1 = __half22float2(fr[2 * q + 1]);
-                        v.z = f1.x; v.w = f1.y;
-                    }
-                }
-                *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 4 * q, kK1)) = v;
+                const float2 f0 = __half22float2(nxt.f[2 * q]), f1 = __half22float2(nxt.f[2 * q + 1]);
+                *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 4 * q, kK1)) = make_float4(f0.x, f0.y, f1.x, f1.y);
             }
             const float xh = __uint_as_float(to_tf32(r.px)), yh = __uint_as_float(to_tf32(r.py)), zh = __uint_as_float(to_tf32(r.pz));
             const float xl = __uint_as_float(to_tf32(r.px - xh)), yl = __uint_as_float(to_tf32(r.py - yh)), zl = __uint_as_float(to_tf32(r.pz - zh));
             *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 32, kK1)) = make_float4(xh, yh, zh, xl);
             *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 36, kK1)) = make_float4(yl, zl, 1.f, 0.f);
         }
+        fetch(q0 + (int64_t)gridDim.x * kTileQ, nxt);      // next tile's loads are in flight from here on
         umma::fence_smem_to_async_proxy();
         umma::fence_before_sync();
         __syncthreads();
