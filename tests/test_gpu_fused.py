@@ -124,10 +124,12 @@ def test_sdf_eval_grad_argument_errors(cuda):
     assert l.snb_sdf_eval_grad(0, None, C.byref(net), None, None, None) == 0     # empty input is a no-op
 
 
-@pytest.mark.parametrize("variance,cut_active,n_active", [(0.3, False, 4), (0.75, True, 4), (0.3, False, 2), (0.3, False, 6)])
-def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active):
-    """n_active >= 3 runs the tcgen05 backward, n_active < 3 the FMA backward (fused_sdf.cu: snb_sdf_bwd_patch)."""
-    ds, osdf, odev, orend, tr, batch_cpu = _setup(cuda, variance=variance, n_active=n_active)
+@pytest.mark.parametrize("variance,cut_active,n_active,enc", [(0.3, False, 4, ENC), (0.75, True, 4, ENC), (0.3, False, 2, ENC), (0.3, False, 6, ENC),
+                                                              (0.3, False, 16, ENC16), (0.3, False, 9, ENC16)])
+def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active, enc):
+    """n_active >= 3 runs the tcgen05 backward, n_active < 3 the FMA backward (fused_sdf.cu: snb_sdf_bwd_patch); 16 levels is the
+    maximum the kernels are compiled for (all 32 feature columns of the MMA tiles live)."""
+    ds, osdf, odev, orend, tr, batch_cpu = _setup(cuda, variance=variance, n_active=n_active, ENC=enc)
     o, d, pn, vinv, nrm, msk = batch_cpu
     batch, near, far = _to_gpu_batch(ds, batch_cpu, cuda)
     step = 0.02
