@@ -320,24 +320,36 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
 //         dz enters as the TF32 tile (rounded to nearest: unbiased, 2^-12 rms per element, averaged over the points); a bf16
 //         side tile for the residual was measured (+14 % kernel time for errors far below the minibatch noise) and dropped.
 // (3) runs on the tensor pipe while the warps do (4).
-constexpr int kK1 = 40;                      // columns of X1: 32 feature slots | x_hi (3) | x_lo (3) | 1 | pad
-constexpr int kColXhi = 32, kColXlo = 35, kColOne = 38;
-constexpr uint32_t kBwdTmemCols = 128;       // Z: columns 0..63, U: 64..95
-constexpr size_t kBwdUmmaSmem = umma::tile_bytes(64, kK1) * 2 + umma::tile_bytes(32, 64) + umma::tile_bytes(128, kK1) + umma::tile_bytes(128, 64);
+// KF = feature slots of the tiles: 32 (up to 16 levels; 80 KB of shared memory, 2 CTAs/SM) or 8 (up to 4 levels; 52 KB, 4 CTAs/SM --
+// the first ~1 400 iterations of the schedule, where a tile's dependent phases are short and latency, not work, sets the pace).
+template <int KF>
+struct BwdCfg {
+    static constexpr int kK1 = KF + 8;                       // columns of X1: KF feature slots | x_hi (3) | x_lo (3) | 1 | pad
+    static constexpr int kColXhi = KF, kColXlo = KF + 3, kColOne = KF + 6;
+    static constexpr int kN2 = KF < 16 ? 16 : KF;            // N of the feature-gradient MMA (multiple of 16 for M = 128)
+    static constexpr int kNMT = (kK1 + 15) / 16;             // 16-column tiles of the weight-gradient mma.sync
+    static constexpr uint32_t kTmemCols = 128;               // Z: columns 0..63, U: 64..64+kN2
+    static constexpr size_t kSmem = umma::tile_bytes(64, kK1) * 2 + umma::tile_bytes(kN2, 64) + umma::tile_bytes(128, kK1) + umma::tile_bytes(128, 64);
+    static constexpr int kMinBlocks = KF <= 8 ? 3 : 2;
+};
 
-__global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
+template <int KF>
+__global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umma_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
                                                                     const __half2 *__restrict__ feats,
                                                                     const float *__restrict__ d_sdf0,
                                                                     const float *__restrict__ d_sdf1,
                                                                     float *__restrict__ table_grad, float *__restrict__ net_grad,
                                                                     int *__restrict__ err_flag) {
+    using Cfg = BwdCfg<KF>;
+    constexpr int kK1 = Cfg::kK1, kColXhi = Cfg::kColXhi, kColXlo = Cfg::kColXlo, kColOne = Cfg::kColOne, kN2 = Cfg::kN2, kNMT = Cfg::kNMT;
+    constexpr uint32_t kBwdTmemCols = Cfg::kTmemCols;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_z, bar_u;
     __shared__ uint32_t s_tmem;
     __shared__ float s_w1[kH];
     __shared__ LevelCtx s_lvl[SNB_MAX_LEVELS];
     uint8_t *b1hi = smem_raw, *b1lo = b1hi + umma::tile_bytes(64, kK1), *b2 = b1lo + umma::tile_bytes(64, kK1);
-    uint8_t *a1 = b2 + umma::tile_bytes(32, 64), *a2 = a1 + umma::tile_bytes(128, kK1);
+    uint8_t *a1 = b2 + umma::tile_bytes(kN2, 64), *a2 = a1 + umma::tile_bytes(128, kK1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const uint32_t L = net.meta.n_levels, n_active = net.n_active;
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
             const int h = e / kK1, k = e % kK1;
             float w = 0.f;
             bool lo_zero = false;
-            if (k < 32) w = __ldg(W + kOffW0T + (3 + k) * kH + h);
+            if (k < KF) w = __ldg(W + kOffW0T + (3 + k) * kH + h);
             else if (k < kColXlo) w = __ldg(W + kOffW0T + (k - kColXhi) * kH + h);
             else if (k < kColOne) { w = __ldg(W + kOffW0T + (k - kColXlo) * kH + h); lo_zero = true; }   // x_lo * W_lo is below 2^-22
             else if (k == kColOne) w = __ldg(W + kOffB0 + h);
@@ -357,9 +369,9 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
             *reinterpret_cast<float *>(b1hi + umma::kmajor_off(h, k, kK1)) = hi;
             *reinterpret_cast<float *>(b1lo + umma::kmajor_off(h, k, kK1)) = lo_zero ? 0.f : __uint_as_float(to_tf32(w - hi));
         }
-        for (int e = tid; e < 32 * 64; e += 128) {
+        for (int e = tid; e < kN2 * 64; e += 128) {
             const int j = e / 64, h = e % 64;
-            *reinterpret_cast<float *>(b2 + umma::kmajor_off(j, h, 64)) = __uint_as_float(to_tf32(__ldg(W + kOffW0T + (3 + j) * kH + h)));
+            *reinterpret_cast<float *>(b2 + umma::kmajor_off(j, h, 64)) = j < KF ? __uint_as_float(to_tf32(__ldg(W + kOffW0T + (3 + j) * kH + h))) : 0.f;
         }
         if (tid < kH) s_w1[tid] = __ldg(W + kOffW1 + tid);
         if (tid < SNB_MAX_LEVELS) s_lvl[tid] = lt.lv[tid];
@@ -374,7 +386,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
     const uint32_t tmem_lane = tmem + ((uint32_t)(32 * warp) << 16);
     const uint32_t a1_addr = umma::smem_u32(a1), a2_addr = umma::smem_u32(a2);
     const uint32_t b1hi_addr = umma::smem_u32(b1hi), b1lo_addr = umma::smem_u32(b1lo), b2_addr = umma::smem_u32(b2);
-    const uint32_t idesc_z = umma::idesc_tf32(128, 64), idesc_u = umma::idesc_tf32(128, 32);
+    const uint32_t idesc_z = umma::idesc_tf32(128, 64), idesc_u = umma::idesc_tf32(128, kN2);
 
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t Q = (int64_t)S + E;                            // sample starts + own interval ends; point p = 9 q + k
@@ -385,10 +397,9 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
     const int tk = tid / kTileQ, tj = tid % kTileQ;
     const int n_feat_steps = (int)(2 * n_active + 7) >> 3;     // feature k-steps of (1) that can be non-zero
     // (4): output tiles [3 m-tiles (input columns 0..15, 16..31, 32..47) x 8 n-tiles (hidden)] dealt to the 4 warps
-    const int n_mt = (2 * (int)n_active > 16) ? 3 : 2;          // m-tile 1 (features 16..31) only when > 8 levels are active
-    float wacc[6][4];
+    float wacc[2 * kNMT][4];
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 2 * kNMT; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) wacc[i][c] = 0.f;
     float accW1a = 0.f, accW1b = 0.f, accB1 = 0.f;
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
     struct TileRegs {
         bool valid;
         float dsdf, px, py, pz;
-        __half2 f[SNB_MAX_LEVELS];
+        __half2 f[KF / 2];
     };
     auto fetch = [&](int64_t q0, TileRegs &o) {
         const int64_t p = (q0 + tj) * SNB_PATCH + tk;
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
         o.dsdf = 0.f;
         o.px = o.py = o.pz = 0.f;
 #pragma unroll
-        for (int l = 0; l < SNB_MAX_LEVELS; ++l) o.f[l] = __float2half2_rn(0.f);
+        for (int l = 0; l < KF / 2; ++l) o.f[l] = __float2half2_rn(0.f);
         if (o.valid) {
             const PointRef r = decode_point(p, S, b, sm);
             o.px = r.px; o.py = r.py; o.pz = r.pz;
@@ -421,7 +432,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
             }
             const __half2 *fr = feats + p * L;
 #pragma unroll
-            for (int l = 0; l < SNB_MAX_LEVELS; ++l)
+            for (int l = 0; l < KF / 2; ++l)
                 if (l < (int)n_active) o.f[l] = fr[l];
         }
     };
@@ -436,14 +447,14 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
         r.px = nxt.px; r.py = nxt.py; r.pz = nxt.pz;
         {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {       // 8 chunks of 4 feature columns (2 levels each)
+            for (int q = 0; q < KF / 4; ++q) {  // chunks of 4 feature columns (2 levels each)
                 const float2 f0 = __half22float2(nxt.f[2 * q]), f1 = __half22float2(nxt.f[2 * q + 1]);
                 *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 4 * q, kK1)) = make_float4(f0.x, f0.y, f1.x, f1.y);
             }
             const float xh = __uint_as_float(to_tf32(r.px)), yh = __uint_as_float(to_tf32(r.py)), zh = __uint_as_float(to_tf32(r.pz));
             const float xl = __uint_as_float(to_tf32(r.px - xh)), yl = __uint_as_float(to_tf32(r.py - yh)), zl = __uint_as_float(to_tf32(r.pz - zh));
-            *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 32, kK1)) = make_float4(xh, yh, zh, xl);
-            *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, 36, kK1)) = make_float4(yl, zl, 1.f, 0.f);
+            *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, KF, kK1)) = make_float4(xh, yh, zh, xl);
+            *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, KF + 4, kK1)) = make_float4(yl, zl, 1.f, 0.f);
         }
         fetch(q0 + (int64_t)gridDim.x * kTileQ, nxt);      // next tile's loads are in flight from here on
         umma::fence_smem_to_async_proxy();
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
         if (tid == 0) {
             uint32_t acc = 0;
             for (int s = 0; s < kK1 / 8; ++s) {
-                if (s < 4 && s >= n_feat_steps) continue;      // all-zero feature columns
+                if (s < KF / 8 && s >= n_feat_steps) continue;   // all-zero feature columns
                 const uint64_t ad = umma::kmajor_desc(a1_addr + 256u * s, kK1);
                 umma::mma_tf32(tmem, ad, umma::kmajor_desc(b1hi_addr + 256u * s, kK1), idesc_z, acc);
                 umma::mma_tf32(tmem, ad, umma::kmajor_desc(b1lo_addr + 256u * s, kK1), idesc_z, 1);
@@ -513,29 +524,24 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
         {
             const uint8_t *ab = a1 + (g >> 2) * 128 + (g & 3) * 4 + t * 16;              // column g of m-tile 0; m-tile mt: + mt * 512
             const uint8_t *bb0 = a2 + (2 * warp + (g >> 2)) * 128 + (g & 3) * 4 + t * 16;  // hidden 8 warp + g; second tile: + 8 * 128
-            const bool m0 = n_active > 0, m1 = n_mt == 3;
 #pragma unroll 2
             for (int ks = 0; ks < 16; ++ks) {
                 const uint8_t *ak = ab + ks * (kK1 / 4) * 128, *bk = bb0 + ks * (64 / 4) * 128;
                 const uint32_t b00 = *reinterpret_cast<const uint32_t *>(bk), b01 = *reinterpret_cast<const uint32_t *>(bk + 64);
                 const uint32_t b10 = *reinterpret_cast<const uint32_t *>(bk + 1024), b11 = *reinterpret_cast<const uint32_t *>(bk + 1024 + 64);
-                uint32_t a[4];
-                if (m0) {
-                    a[0] = *reinterpret_cast<const uint32_t *>(ak); a[1] = *reinterpret_cast<const uint32_t *>(ak + 256);
-                    a[2] = *reinterpret_cast<const uint32_t *>(ak + 64); a[3] = *reinterpret_cast<const uint32_t *>(ak + 256 + 64);
-                    mma_tf32(wacc[0], a, b00, b01);
-                    mma_tf32(wacc[1], a, b10, b11);
+#pragma unroll
+                for (int mt = 0; mt < kNMT; ++mt) {
+                    // a feature-only tile whose columns are all beyond the active levels contributes nothing
+                    if (16 * mt + 16 <= KF && 16 * mt >= 2 * (int)n_active) continue;
+                    const bool hi_half = 16 * mt + 8 < kK1;          // columns 16 mt + 8 .. + 15 exist
+                    uint32_t a[4];
+                    a[0] = *reinterpret_cast<const uint32_t *>(ak + mt * 512);
+                    a[2] = *reinterpret_cast<const uint32_t *>(ak + mt * 512 + 64);
+                    a[1] = hi_half ? *reinterpret_cast<const uint32_t *>(ak + mt * 512 + 256) : 0u;
+                    a[3] = hi_half ? *reinterpret_cast<const uint32_t *>(ak + mt * 512 + 256 + 64) : 0u;
+                    mma_tf32(wacc[2 * mt], a, b00, b01);
+                    mma_tf32(wacc[2 * mt + 1], a, b10, b11);
                 }
-                if (m1) {
-                    a[0] = *reinterpret_cast<const uint32_t *>(ak + 512); a[1] = *reinterpret_cast<const uint32_t *>(ak + 512 + 256);
-                    a[2] = *reinterpret_cast<const uint32_t *>(ak + 512 + 64); a[3] = *reinterpret_cast<const uint32_t *>(ak + 512 + 256 + 64);
-                    mma_tf32(wacc[2], a, b00, b01);
-                    mma_tf32(wacc[3], a, b10, b11);
-                }
-                a[0] = *reinterpret_cast<const uint32_t *>(ak + 1024); a[1] = 0u;       // columns 32..39; 40..47 do not exist
-                a[2] = *reinterpret_cast<const uint32_t *>(ak + 1024 + 64); a[3] = 0u;
-                mma_tf32(wacc[4], a, b00, b01);
-                mma_tf32(wacc[5], a, b10, b11);
             }
         }
 
@@ -606,13 +612,13 @@ __global__ void __launch_bounds__(128, 2) sdf_bwd_patch_umma_kernel(snb_patch_ba
 
     // ---- flush
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 2 * kNMT; ++i) {
         const int mt = i >> 1, nt = warp + 4 * (i & 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int col = 16 * mt + g + 8 * (c >> 1), h = 8 * nt + 2 * t + (c & 1);
             float *dst = nullptr;
-            if (col < 32) { if (col < 2 * (int)n_active) dst = net_grad + kOffW0T + (3 + col) * kH + h; }
+            if (col < KF) { if (col < 2 * (int)n_active) dst = net_grad + kOffW0T + (3 + col) * kH + h; }
             else if (col < kColXlo) dst = net_grad + kOffW0T + (col - kColXhi) * kH + h;
             else if (col < kColOne) dst = net_grad + kOffW0T + (col - kColXlo) * kH + h;
             else if (col == kColOne) dst = net_grad + kOffB0 + h;
@@ -712,21 +718,25 @@ extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *ne
     SNB_REQUIRE(feats && d_sdf0 && d_sdf1 && table_grad && net_grad, SNB_ERR_NULL, "sdf_bwd_patch: null buffer");
     SNB_REQUIRE(aligned(table_grad, 8), SNB_ERR_ALIGN, "sdf_bwd_patch: table_grad must be 8-byte aligned");
     static const size_t smem = sizeof(float) * (kNetFloats + kTile * kDzStride + kTile * kXStride);
-    // tcgen05 kernel from 3 active levels on (measured: 104 vs 113 us at 4 levels, 432 vs 532 us at 14; the FMA kernel is ahead at
-    // 1-2 levels, where neither GEMMs nor atomics dominate).  SNB_BWD_UMMA=0 / 1 forces one of them (cross-checks).
-    static const int force_umma = getenv("SNB_BWD_UMMA") ? atoi(getenv("SNB_BWD_UMMA")) : -1;
-    const int use_umma = force_umma >= 0 ? force_umma : (net->n_active >= 3);
+    // tcgen05 kernel (KF = 8 tiles up to 4 active levels, KF = 32 beyond): 140 vs 178 us at 1 level, 75 vs 113 us at 4, 370 vs 532 us
+    // at 14 against the FMA kernel, which SNB_BWD_UMMA=0 still selects for cross-checks (tests/test_gpu_fused.py).
+    static const int use_umma = getenv("SNB_BWD_UMMA") ? atoi(getenv("SNB_BWD_UMMA")) : 1;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(sdf_bwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(sdf_bwd_patch_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
+        cudaFuncSetAttribute(sdf_bwd_patch_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg<32>::kSmem);
+        cudaFuncSetAttribute(sdf_bwd_patch_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg<8>::kSmem);
         configured = true;
     }
-    if (use_umma)
-        sdf_bwd_patch_umma_kernel<<<kNumSMs * 2, 128, kBwdUmmaSmem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1,
-                                                                                    table_grad, net_grad, sm->totals + 2);
+    const LevelTable ltab = make_level_table(net->meta);
+    if (use_umma && net->n_active <= 4)
+        sdf_bwd_patch_umma_kernel<8><<<kNumSMs * BwdCfg<8>::kMinBlocks, 128, BwdCfg<8>::kSmem, S(stream)>>>(*b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1,
+                                                                                                            table_grad, net_grad, sm->totals + 2);
+    else if (use_umma)
+        sdf_bwd_patch_umma_kernel<32><<<kNumSMs * BwdCfg<32>::kMinBlocks, 128, BwdCfg<32>::kSmem, S(stream)>>>(*b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1,
+                                                                                                               table_grad, net_grad, sm->totals + 2);
     else
-        sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
+        sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
     SNB_LAUNCH_CHECK("sdf_bwd_patch");
     return SNB_OK;
 }

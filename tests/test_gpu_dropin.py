@@ -35,8 +35,10 @@ def test_dropin_step_matches_reference_kernels(cuda):
         assert abs(la - lb) <= 5e-3 * abs(la) + 1e-5, (la, lb)   # fp32 atomics reorder run to run; Adam amplifies it on near-zero gradients
         if na_ == nb:   # identical sample lists -> rendered normals agree to fp32 rounding of the scatter order
             assert torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])
-            # step 0 agrees to fp32 rounding; later steps carry the run-to-run reordering of fp32 atomics through Adam
-            assert torch.allclose(ca, cb, atol=2e-4 if step_i == 0 else 2e-3, rtol=1e-3)
+            # step 0 agrees to fp32 rounding.  Later steps start from parameters that already differ: the two backends add the
+            # table gradients in different orders and Adam's m / (sqrt(v) + eps) turns a rounding-level difference of a near-zero
+            # gradient into a full +-lr step of that parameter, so rendered normals may drift by O(steps * lr) = 1e-2.
+            assert torch.allclose(ca, cb, atol=2e-4 if step_i == 0 else 2e-2, rtol=1e-3)
 
 
 def test_dropin_first_step_bit_identical_samples(cuda):

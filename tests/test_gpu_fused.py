@@ -127,8 +127,8 @@ def test_sdf_eval_grad_argument_errors(cuda):
 @pytest.mark.parametrize("variance,cut_active,n_active,enc", [(0.3, False, 4, ENC), (0.75, True, 4, ENC), (0.3, False, 2, ENC), (0.3, False, 6, ENC),
                                                               (0.3, False, 16, ENC16), (0.3, False, 9, ENC16)])
 def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active, enc):
-    """n_active >= 3 runs the tcgen05 backward, n_active < 3 the FMA backward (fused_sdf.cu: snb_sdf_bwd_patch); 16 levels is the
-    maximum the kernels are compiled for (all 32 feature columns of the MMA tiles live)."""
+    """The backward is the tcgen05 kernel (8-column tiles up to 4 active levels, 32-column tiles beyond; 16 levels is the maximum the
+    kernels are compiled for).  test_fma_backward_cross_check reruns two cases on the FMA kernel (SNB_BWD_UMMA=0)."""
     ds, osdf, odev, orend, tr, batch_cpu = _setup(cuda, variance=variance, n_active=n_active, ENC=enc)
     o, d, pn, vinv, nrm, msk = batch_cpu
     batch, near, far = _to_gpu_batch(ds, batch_cpu, cuda)
@@ -224,7 +224,7 @@ def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active, 
     tr.buf.stats[4] = 0.0
     call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(tr.buf.stats), ptr(m.grad))
     got = flat_grads()
-    # The tcgen05 backward (>= 3 active levels) forms d loss/d features (-> table) and dW0 / db0 from dz rounded to TF32 (round to
+    # The tcgen05 backward forms d loss/d features (-> table) and dW0 / db0 from dz rounded to TF32 (round to
     # nearest: unbiased, 2^-12 rms relative per element -- the precision class of the fp16 dL/dy tiny-cuda-nn's own backward
     # consumes); sums over 64 hidden units / many points average that down.  z recompute, dW1, db1 are fp32-accurate.
     for k, tol, tol_max in (("table", 6e-4, 2e-3), ("g0", 5e-4, 1e-3), ("v0", 5e-4, 1e-3), ("b0", 5e-4, 1e-3), ("g1", 2e-4, 5e-4), ("v1", 2e-4, 5e-4)):
@@ -415,3 +415,14 @@ def test_host_batch_feeder_matches_device_batches(cuda):
         assert g["overflow"] == 0 and abs(g["n_samples"] - r["n_samples"]) <= max(3, 0.01 * r["n_samples"])
         assert abs(g["loss"] - r["loss"]) <= 5e-3 * max(1.0, abs(r["loss"]))
     assert (a.model.flat - b.model.flat).abs().max() <= 5 * 5e-4 * 2   # bounded by steps * lr per parameter
+
+
+def test_fma_backward_cross_check(cuda):
+    """The thread-per-point FMA backward (the pre-tcgen05 kernel, kept as the independent implementation) still passes the oracle
+    parity cases: the kernel choice is read once per process from SNB_BWD_UMMA, hence the subprocess."""
+    import os, subprocess, sys
+    env = dict(os.environ, SNB_BWD_UMMA="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "test_fused_forward_backward_vs_oracle and (0.3-False-2 or 0.3-False-6)"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:]
