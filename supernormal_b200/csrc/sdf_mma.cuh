@@ -117,10 +117,34 @@ __device__ __forceinline__ float warp_layer1(const float (&acc)[2][8][4], float 
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const float2 w1 = *reinterpret_cast<const float2 *>(s_net + kOffW1 + 8 * nt + 2 * t);
+        // saturation shortcut per group of 8 values (one vote instead of eight): a group that is saturated in every lane is
+        // max(z, 0); otherwise all 8 softplus are evaluated branch-free, back to back, so their MUFU latencies overlap
+        bool sat = SAT;
+        if (SAT) {
+            bool near0 = false;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            part[r] = fmaf(w1.x, softplus100<SAT>(acc[r >> 1][nt][2 * (r & 1)]), part[r]);
-            part[r] = fmaf(w1.y, softplus100<SAT>(acc[r >> 1][nt][2 * (r & 1) + 1]), part[r]);
+            for (int r = 0; r < 4; ++r)
+                near0 = near0 || fabsf(100.f * acc[r >> 1][nt][2 * (r & 1)]) < kSoftplusSat || fabsf(100.f * acc[r >> 1][nt][2 * (r & 1) + 1]) < kSoftplusSat;
+            sat = !__any_sync(0xffffffffu, near0);
+        }
+        if (sat) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                part[r] = fmaf(w1.x, fmaxf(acc[r >> 1][nt][2 * (r & 1)], 0.f), part[r]);
+                part[r] = fmaf(w1.y, fmaxf(acc[r >> 1][nt][2 * (r & 1) + 1], 0.f), part[r]);
+            }
+        } else {
+            float sp[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                sp[2 * r] = softplus100<false>(acc[r >> 1][nt][2 * (r & 1)]);
+                sp[2 * r + 1] = softplus100<false>(acc[r >> 1][nt][2 * (r & 1) + 1]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                part[r] = fmaf(w1.x, sp[2 * r], part[r]);
+                part[r] = fmaf(w1.y, sp[2 * r + 1], part[r]);
+            }
         }
     }
 #pragma unroll
