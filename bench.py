@@ -300,7 +300,7 @@ def main():
                                 "traffic": traffic, "traffic_note": traffic_note, "peak_source": which, "algorithmic_bytes_per_launch": dk["bytes"],
                                 "avg_us": dk["us"],
                                 "note": "the step's kernels are latency / issue / L2-atomic bound at 2048 patches per GPU (DESIGN.md section 5); the only HBM-streaming "
-                                        "kernel is the Adam sweep (snb_train_optim in kernels.hbm_model)"}
+                                        "kernel is the Adam sweep inside the step-tail kernel (snb_train_tail in kernels.hbm_model)"}
         if Kr > 0:
             ours_ms = ev0.elapsed_time(evr) / Kr
             for backend, key in (("reference", "reference_cuda_path"), ("dropin", "dropin_api_path")):

@@ -201,6 +201,10 @@ int32_t snb_march_visible(const snb_patch_batch *h_batch, const snb_net *h_net, 
                           snb_stream_t stream);
 /* scan counts -> packed_info/totals, then copy scratch -> packed arrays, assign end slots */
 int32_t snb_compact_samples(int32_t n_patches, const snb_samples *h_samples, snb_stream_t stream);
+/* Same, and the scan CTA also resets the loss accumulators of the iteration: stats[0] = #(mask > 0.5) + 1e-5 (the
+ * normal-loss normaliser, exp_runner.py:184-186), stats[1..7] = 0 -- what snb_prep_net does when given a mask. */
+int32_t snb_compact_samples_stats(int32_t n_patches, const snb_samples *h_samples, int32_t n_mask, const float *mask,
+                                  float *stats, snb_stream_t stream);
 /* SDF at arbitrary points, no grad.  mode 0: sdf, 1: sigmoid(-80*sdf) (models/renderer.py:56-60), 2: -sdf */
 int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *h_net, int32_t mode, float *out, snb_stream_t stream);
 /* self-test of the tcgen05 / TMEM plumbing the fused kernels build on: D[128,N] = A[128,K] * B[N,K]^T, kind::tf32 (operands are
@@ -309,6 +313,24 @@ int32_t snb_train_fwd_bwd(const snb_train_ctx *h_ctx, float step_size, float ear
                           float mask_weight, float eikonal_weight, snb_stream_t stream);
 /* Adam over the MLP/variance parameters and the active levels of the table (exp_runner.py:207) */
 int32_t snb_train_optim(const snb_train_ctx *h_ctx, float lr, int32_t step_count, float grad_scale, snb_stream_t stream);
+
+/* The lean iteration (what FusedTrainer runs by default).  Precondition: net.net holds the folded weights of the current
+ * parameters and net_grad is zero -- both are left behind by snb_train_tail (or by snb_prep_net + a memset).
+ * march_visible -> compact_samples_stats -> sdf_fwd_patch -> render_fused -> sdf_bwd_patch; the gradient w.r.t. the
+ * FOLDED MLP weights stays in net_grad, the table gradient in flat_grad + small_pad. */
+int32_t snb_train_fwd_bwd_lean(const snb_train_ctx *h_ctx, float step_size, float early_stop_eps, float normal_weight,
+                               float mask_weight, float eikonal_weight, snb_stream_t stream);
+/* Everything between the backward of one iteration and the marcher of the next in ONE launch (exp_runner.py:205-207 +
+ * the next iteration's models/fields.py:66-67 weight_norm and dataset_loader.py:223-297 gen_random_patches):
+ *   block 0: weight-norm backward net_grad -> (v, g, b, variance) gradients (skipped if grads_unfolded != 0: flat_grad
+ *            already holds them, e.g. after snb_unfold_grads + a data-parallel allreduce), Adam on that block, fold of
+ *            the updated parameters into net.net, net_grad zeroed;
+ *   next blocks: snb_sample_patches for (seed, next_step) into h_out_next (skipped if h_ds_next is null);
+ *   rest: Adam + gradient zeroing + fp16 refresh over the live table levels.
+ * Results are bit-identical to snb_unfold_grads -> snb_train_optim -> snb_prep_net -> snb_sample_patches. */
+int32_t snb_train_tail(const snb_train_ctx *h_ctx, float lr, int32_t step_count, float grad_scale, int32_t grads_unfolded,
+                       const snb_dataset *h_ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,
+                       const snb_batch_out *h_out_next, snb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Mesh extraction.  Replaces extract_fields / extract_geometry (models/renderer.py:9-34): the 64^3-chunked SDF query

@@ -87,7 +87,7 @@ def stream() -> int:
 LAUNCH_COUNT = 0
 # kernels launched per entry point (memsets not counted)
 KERNELS = {"snb_occgrid_binarize": 2, "snb_compact_samples": 2, "snb_max_i64": 2, "snb_train_fwd_bwd": 8,
-           "snb_train_optim": 1, "snb_occgrid_update_fused": 3}
+           "snb_train_optim": 1, "snb_occgrid_update_fused": 3, "snb_train_fwd_bwd_lean": 5, "snb_train_tail": 1}
 
 
 PROFILE = None  # set to a list to record (name, start_event, end_event) around every call

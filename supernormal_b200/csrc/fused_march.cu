@@ -252,8 +252,15 @@ __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_bat
 }
 
 // One CTA: exclusive scans of the sample counts and the end counts, clipped to the capacities.
-__global__ void __launch_bounds__(1024) scan_counts_kernel(int32_t n, snb_samples sm) {
+// With `stats`: also what prep_net does for the loss accumulators -- stats[0] = number of foreground pixels of the batch + 1e-5
+// (the normal-loss normaliser, exp_runner.py:184-186), stats[1..7] = 0.
+__global__ void __launch_bounds__(1024) scan_counts_kernel(int32_t n, snb_samples sm, int32_t n_mask, const float *__restrict__ mask,
+                                                           float *__restrict__ stats) {
     __shared__ int32_t wsum[2][32];
+    __shared__ float msum[32];
+    float mcount = 0.f;
+    if (stats)
+        for (int e = threadIdx.x; e < n_mask; e += 1024) mcount += mask[e] > 0.5f ? 1.f : 0.f;
     __shared__ int32_t carry[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 2) carry[threadIdx.x] = 0;
@@ -302,6 +309,19 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(int32_t n, snb_sample
         if (threadIdx.x == 1023) { carry[0] = incl[0]; carry[1] = incl[1]; }
         __syncthreads();
     }
+    if (stats) {   // 0/1 counts: exact in fp32 in any order (n_mask < 2^24)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mcount += __shfl_xor_sync(0xffffffffu, mcount, o);
+        if (lane == 0) msum[warp] = mcount;
+        __syncthreads();
+        if (warp == 0) {
+            float t = msum[lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) stats[0] = t + 1e-5f;
+            else if (lane < 8) stats[lane] = 0.f;
+        }
+    }
     if (threadIdx.x == 0) {
         if (carry[0] > sm.capacity || carry[1] > sm.end_capacity) sm.totals[2] = 1;
         sm.totals[0] = (int32_t)min((int64_t)carry[0], sm.capacity);
@@ -312,12 +332,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(int32_t n, snb_sample
 // warp per ray: scratch -> packed (t0,t1,patch id), end-slot assignment.
 // An interval needs its own end query iff t1[i] != t0[i+1] (models/renderer.py:152-154); the last sample of a
 // ray always does (the reference compares it with the next ray's first start, which never matches).
-__global__ void __launch_bounds__(256) compact_kernel(int32_t n, snb_samples sm) {
-    const int lane = threadIdx.x & 31;
-    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (ray >= n) return;
-    const int base = sm.packed_info[2 * ray], cnt = sm.packed_info[2 * ray + 1];
-    const int ebase = sm.end_packed[2 * ray], ecnt = sm.end_packed[2 * ray + 1];
+__device__ __forceinline__ void compact_ray(const snb_samples &sm, int ray, int lane, int base, int cnt, int ebase, int ecnt) {
     const float *sc0 = sm.scratch_t0 + (int64_t)ray * sm.scratch_stride;
     const float *sc1 = sm.scratch_t1 + (int64_t)ray * sm.scratch_stride;
     int eused = 0;
@@ -344,6 +359,94 @@ __global__ void __launch_bounds__(256) compact_kernel(int32_t n, snb_samples sm)
     }
 }
 
+__global__ void __launch_bounds__(256) compact_kernel(int32_t n, snb_samples sm) {
+    const int lane = threadIdx.x & 31;
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ray >= n) return;
+    compact_ray(sm, ray, lane, sm.packed_info[2 * ray], sm.packed_info[2 * ray + 1], sm.end_packed[2 * ray], sm.end_packed[2 * ray + 1]);
+}
+
+// scan + compaction + loss-accumulator reset in ONE launch (n <= kCompactOneMax rays): every CTA (8 rays, warp per ray) sums the
+// counts of the rays in front of it itself -- n/8 CTAs x n counts from L2 instead of a single-CTA scan kernel and a second launch --
+// and one extra CTA counts the foreground pixels (stats[0]) and zeroes stats[1..7].  Same outputs as scan_counts_kernel + compact_kernel.
+constexpr int kCompactOneMax = 4096;
+__global__ void __launch_bounds__(256) compact_one_kernel(int32_t n, snb_samples sm, int32_t n_mask, const float *__restrict__ mask,
+                                                          float *__restrict__ stats) {
+    __shared__ int32_t s_part[2][8];
+    __shared__ int32_t s_cnt[2][8];
+    __shared__ float s_m[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_ctas = (n + 7) >> 3;
+    if ((int)blockIdx.x == n_ctas) {   // ---- stats CTA ----
+        if (!stats) return;
+        float c = 0.f;
+        if ((reinterpret_cast<uintptr_t>(mask) & 15) == 0) {
+            const float4 *m4 = reinterpret_cast<const float4 *>(mask);
+            for (int e = threadIdx.x; e < (n_mask >> 2); e += 256) {
+                float4 v = __ldg(m4 + e);
+                c += (v.x > 0.5f ? 1.f : 0.f) + (v.y > 0.5f ? 1.f : 0.f) + (v.z > 0.5f ? 1.f : 0.f) + (v.w > 0.5f ? 1.f : 0.f);
+            }
+            for (int e = (n_mask & ~3) + threadIdx.x; e < n_mask; e += 256) c += mask[e] > 0.5f ? 1.f : 0.f;
+        } else {
+            for (int e = threadIdx.x; e < n_mask; e += 256) c += mask[e] > 0.5f ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);   // 0/1 counts: exact in fp32 in any order
+        if (lane == 0) s_m[warp] = c;
+        __syncthreads();
+        if (warp == 0) {
+            float t = lane < 8 ? s_m[lane] : 0.f;
+#pragma unroll
+            for (int o = 4; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) stats[0] = t + 1e-5f;
+            else if (lane < 8) stats[lane] = 0.f;
+        }
+        return;
+    }
+    // ---- sum of the counts in front of this CTA's 8 rays, and the 8 own counts ----
+    const int first = blockIdx.x * 8;
+    int32_t a0 = 0, a1 = 0;
+    for (int i = threadIdx.x; i < first; i += 256) { a0 += sm.counts[i]; a1 += sm.end_counts[i]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    const int ray = first + warp;
+    if (lane == 0) {
+        s_part[0][warp] = a0; s_part[1][warp] = a1;
+        s_cnt[0][warp] = ray < n ? sm.counts[ray] : 0;
+        s_cnt[1][warp] = ray < n ? sm.end_counts[ray] : 0;
+    }
+    __syncthreads();
+    int64_t off[2] = {0, 0};
+    int32_t own[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) off[a] += s_part[a][w] + (w < warp ? s_cnt[a][w] : 0);
+        own[a] = s_cnt[a][warp];
+    }
+    if ((int)blockIdx.x == n_ctas - 1 && warp == 7 && lane == 0) {   // totals (off + own of the last warp slot = grand totals)
+        int64_t t0 = off[0] + own[0], t1 = off[1] + own[1];
+        if (t0 > sm.capacity || t1 > sm.end_capacity) sm.totals[2] = 1;
+        sm.totals[0] = (int32_t)min(t0, sm.capacity);
+        sm.totals[1] = (int32_t)min(t1, sm.end_capacity);
+    }
+    if (ray >= n) return;
+    const int64_t cap[2] = {sm.capacity, sm.end_capacity};
+    int32_t boff[2], bcnt[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {   // clip to the capacities exactly like scan_counts_kernel
+        int64_t o = off[a], c = own[a];
+        if (o >= cap[a]) { o = cap[a]; c = 0; }
+        else if (o + c > cap[a]) c = cap[a] - o;
+        boff[a] = (int32_t)o; bcnt[a] = (int32_t)c;
+    }
+    if (lane == 0) {
+        sm.packed_info[2 * ray] = boff[0]; sm.packed_info[2 * ray + 1] = bcnt[0];
+        sm.end_packed[2 * ray] = boff[1]; sm.end_packed[2 * ray + 1] = bcnt[1];
+    }
+    compact_ray(sm, ray, lane, boff[0], bcnt[0], boff[1], bcnt[1]);
+}
+
 }  // namespace snb
 using namespace snb;
 
@@ -364,11 +467,28 @@ extern "C" int32_t snb_march_visible(const snb_patch_batch *b, const snb_net *ne
     return SNB_OK;
 }
 
+extern "C" int32_t snb_compact_samples_stats(int32_t n, const snb_samples *sm, int32_t n_mask, const float *mask, float *stats,
+                                             snb_stream_t stream) {
+    SNB_REQUIRE(sm, SNB_ERR_NULL, "compact_samples: null struct");
+    SNB_REQUIRE(n >= 0 && n_mask >= 0 && n_mask < (1 << 24), SNB_ERR_ARG, "compact_samples: bad n / n_mask");
+    SNB_REQUIRE(sm->packed_info && sm->end_packed && sm->t0 && sm->t1 && sm->patch_idx && sm->end_slot && sm->slot_sample, SNB_ERR_NULL, "compact_samples: null buffer");
+    SNB_REQUIRE(!stats || n_mask == 0 || mask, SNB_ERR_NULL, "compact_samples: null mask");
+    if (n > 0 && n <= kCompactOneMax) {   // one launch: per-CTA prefix sums (n^2/8 count reads from L2) + one stats CTA
+        compact_one_kernel<<<(unsigned)cdiv(n, 8) + 1, 256, 0, S(stream)>>>(n, *sm, n_mask, mask, stats);
+    } else {
+        scan_counts_kernel<<<1, 1024, 0, S(stream)>>>(n, *sm, n_mask, mask, stats);
+        if (n) compact_kernel<<<(unsigned)cdiv(n, 8), 256, 0, S(stream)>>>(n, *sm);
+    }
+    SNB_LAUNCH_CHECK("compact_samples");
+    return SNB_OK;
+}
+
+// the two-launch form (single-CTA scan, then compaction), any n
 extern "C" int32_t snb_compact_samples(int32_t n, const snb_samples *sm, snb_stream_t stream) {
     SNB_REQUIRE(sm, SNB_ERR_NULL, "compact_samples: null struct");
     SNB_REQUIRE(n >= 0, SNB_ERR_ARG, "compact_samples: n < 0");
     SNB_REQUIRE(sm->packed_info && sm->end_packed && sm->t0 && sm->t1 && sm->patch_idx && sm->end_slot && sm->slot_sample, SNB_ERR_NULL, "compact_samples: null buffer");
-    scan_counts_kernel<<<1, 1024, 0, S(stream)>>>(n, *sm);
+    scan_counts_kernel<<<1, 1024, 0, S(stream)>>>(n, *sm, 0, nullptr, nullptr);
     if (n) compact_kernel<<<(unsigned)cdiv(n, 8), 256, 0, S(stream)>>>(n, *sm);
     SNB_LAUNCH_CHECK("compact_samples");
     return SNB_OK;

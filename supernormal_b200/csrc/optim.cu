@@ -1,6 +1,6 @@
 // optim.cu -- parameter plumbing of the fused step: weight-norm folding (models/fields.py:66-67),
 // variance network (models/fields.py:133-139), their backward, and Adam (exp_runner.py:97,205-207).
-#include "sdf_core.cuh"
+#include "sampler.cuh"
 
 namespace snb {
 
@@ -22,37 +22,123 @@ __device__ __forceinline__ float block_sum(float v, float *s_red) {
     return warp_sum_f(t);
 }
 
+// ---- building blocks shared by the stand-alone kernels and the step-tail kernel (generic pointers: global or shared) ----
+
+struct SmallLayout {   // offsets inside `small` = v0[64, d_in] | g0[64] | b0[64] | v1[64] | g1 | b1 | variance
+    int d_in, g0, b0, v1, g1, b1, var, n;
+    __device__ __forceinline__ explicit SmallLayout(int n_levels) {
+        d_in = 3 + 2 * n_levels;
+        g0 = kH * d_in; b0 = g0 + kH; v1 = b0 + kH; g1 = v1 + kH; b1 = g1 + 1; var = b1 + 1; n = var + 1;
+    }
+};
+
+// |v0[row]| of one lin0 row, lanes over the input features; every lane gets the result
+__device__ __forceinline__ float row_sumsq(const float *v, int d_in, int lane) {
+    float ss = 0.f;
+    for (int i = lane; i < d_in; i += 32) ss += v[i] * v[i];
+    return warp_sum_f(ss);
+}
+
+// folded lin0 / lin1 / variance -> net (models/fields.py:66-67,133-139); s_norm[64] = |v0[row]|, n1 = |v1|
+__device__ __forceinline__ void fold_store(const SmallLayout &L, const float *small, const float *s_norm, float n1, float *__restrict__ net,
+                                           int tid, int nthreads) {
+    const float *v0 = small, *g0 = small + L.g0, *b0 = small + L.b0, *v1 = small + L.v1;
+    for (int e = tid; e < kDinMax * kH; e += nthreads) {
+        int i = e / kH, h = e % kH;
+        net[kOffW0T + e] = i < L.d_in ? g0[h] * v0[h * L.d_in + i] / s_norm[h] : 0.f;
+    }
+    if (tid < kH) {
+        net[kOffB0 + tid] = b0[tid];
+        net[kOffW1 + tid] = small[L.g1] * v1[tid] / n1;
+    }
+    if (tid == 0) {
+        net[kOffB1] = small[L.b1];
+        net[kOffInvS] = fminf(fmaxf(expf(small[L.var] * 10.f), 1e-6f), 1e6f);
+    }
+    for (int e = kOffInvS + 1 + tid; e < kNetFloats; e += nthreads) net[e] = 0.f;
+}
+
+// one lin0 row of the weight-norm backward:  W = g v/|v|  ->  dg = <dW,v>/|v|,  dv = g/|v| (dW - <dW,v> v/|v|^2)
+__device__ __forceinline__ void unfold_row(const SmallLayout &L, int row, int lane, const float *small, const float *net_grad, float *small_grad) {
+    const float *v = small + row * L.d_in;
+    float ss = 0.f, dot = 0.f;
+    for (int i = lane; i < L.d_in; i += 32) {
+        float vi = v[i];
+        ss += vi * vi;
+        dot += net_grad[kOffW0T + i * kH + row] * vi;
+    }
+    ss = warp_sum_f(ss);
+    dot = warp_sum_f(dot);
+    float nrm = sqrtf(ss), g = small[L.g0 + row];
+    for (int i = lane; i < L.d_in; i += 32) small_grad[row * L.d_in + i] = g / nrm * (net_grad[kOffW0T + i * kH + row] - dot * v[i] / ss);
+    if (lane == 0) {
+        small_grad[L.g0 + row] = dot / nrm;
+        small_grad[L.b0 + row] = net_grad[kOffB0 + row];
+    }
+}
+
+// lin1 (one row of 64), biases, variance: ss1 = |v1|^2, dot1 = <dW1, v1> (block-wide sums, identical in every thread)
+__device__ __forceinline__ void unfold_tail(const SmallLayout &L, int tid, float ss1, float dot1, const float *small, const float *net_grad,
+                                            float d_inv_s, float *small_grad) {
+    float n1 = sqrtf(ss1), g1 = small[L.g1];
+    if (tid < kH) small_grad[L.v1 + tid] = g1 / n1 * (net_grad[kOffW1 + tid] - dot1 * small[L.v1 + tid] / ss1);
+    if (tid == 0) {
+        small_grad[L.g1] = dot1 / n1;
+        small_grad[L.b1] = net_grad[kOffB1];
+        float e = expf(small[L.var] * 10.f);
+        small_grad[L.var] = (e >= 1e-6f && e <= 1e6f) ? d_inv_s * 10.f * e : 0.f;
+    }
+}
+
+// torch.optim.Adam (no amsgrad / weight decay): p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+struct AdamCoef { float b1, b2, eps, step, rsqrt_bc2, gscale; };
+__device__ __forceinline__ void adam_elem(const AdamCoef &c, float &p, float g, float &m, float &v) {
+    // explicit roundings: the same bits wherever this is inlined (the compiler may otherwise fuse either product of a*b + c*d)
+    const float gr = __fmul_rn(g, c.gscale);
+    m = __fmaf_rn(c.b1, m, __fmul_rn(1.f - c.b1, gr));
+    v = __fmaf_rn(c.b2, v, __fmul_rn(__fmul_rn(1.f - c.b2, gr), gr));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(c.step, m), __fmaf_rn(sqrtf(v), c.rsqrt_bc2, c.eps)));
+}
+
+// Adam over float4 elements [i0, i1) of the flat buffers + gradient zeroing + fp16 refresh from float f16_start on
+__device__ __forceinline__ void adam_sweep4(const AdamCoef &c, int64_t i0, int64_t i1, int64_t first, int64_t stride, float *__restrict__ p,
+                                            float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, __half *__restrict__ p16,
+                                            int64_t f16_start) {
+    for (int64_t i = i0 + first; i < i1; i += stride) {
+        float4 P = reinterpret_cast<float4 *>(p)[i], G = reinterpret_cast<float4 *>(g)[i];
+        float4 M = reinterpret_cast<float4 *>(m)[i], V = reinterpret_cast<float4 *>(v)[i];
+        adam_elem(c, P.x, G.x, M.x, V.x);
+        adam_elem(c, P.y, G.y, M.y, V.y);
+        adam_elem(c, P.z, G.z, M.z, V.z);
+        adam_elem(c, P.w, G.w, M.w, V.w);
+        reinterpret_cast<float4 *>(p)[i] = P;
+        reinterpret_cast<float4 *>(m)[i] = M;
+        reinterpret_cast<float4 *>(v)[i] = V;
+        reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p16 && 4 * i >= f16_start) {   // fp16 copy of the parameters from f16_start on (the hash table behind the MLP block)
+            __half2 *q = reinterpret_cast<__half2 *>(p16 + (4 * i - f16_start));
+            q[0] = __floats2half2_rn(P.x, P.y);
+            q[1] = __floats2half2_rn(P.z, P.w);
+        }
+    }
+}
+
 // one CTA, 1024 threads: warp w owns rows 2w, 2w+1 of lin0 (lanes over the input features)
 __global__ void __launch_bounds__(kPrepThreads) prep_net_kernel(int n_levels, const float *__restrict__ small, float *__restrict__ net,
                                                                 int n_mask, const float *__restrict__ mask, float *__restrict__ stats) {
     __shared__ float s_norm[kH];
     __shared__ float s_red[32];
-    const int d_in = 3 + 2 * n_levels;
-    const float *v0 = small, *g0 = v0 + kH * d_in, *b0 = g0 + kH, *v1 = b0 + kH, *g1 = v1 + kH, *b1 = g1 + 1, *var = b1 + 1;
+    const SmallLayout L(n_levels);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const int row = 2 * warp + q;
-        float ss = 0.f;
-        for (int i = lane; i < d_in; i += 32) ss += v0[row * d_in + i] * v0[row * d_in + i];
-        ss = warp_sum_f(ss);
+        float ss = row_sumsq(small + row * L.d_in, L.d_in, lane);
         if (lane == 0) s_norm[row] = sqrtf(ss);
     }
-    float part = tid < kH ? v1[tid] * v1[tid] : 0.f;
+    float part = tid < kH ? small[L.v1 + tid] * small[L.v1 + tid] : 0.f;
     float n1 = sqrtf(block_sum(part, s_red));   // also orders s_norm
-    for (int e = tid; e < kDinMax * kH; e += kPrepThreads) {
-        int i = e / kH, h = e % kH;
-        net[kOffW0T + e] = i < d_in ? g0[h] * v0[h * d_in + i] / s_norm[h] : 0.f;
-    }
-    if (tid < kH) {
-        net[kOffB0 + tid] = b0[tid];
-        net[kOffW1 + tid] = g1[0] * v1[tid] / n1;
-    }
-    if (tid == 0) {
-        net[kOffB1] = b1[0];
-        net[kOffInvS] = fminf(fmaxf(expf(var[0] * 10.f), 1e-6f), 1e6f);
-    }
-    for (int e = kOffInvS + 1 + tid; e < kNetFloats; e += kPrepThreads) net[e] = 0.f;
+    fold_store(L, small, s_norm, n1, net, tid, kPrepThreads);
     if (stats) {
         float m = 0.f;
         for (int e = tid; e < n_mask; e += kPrepThreads) m += mask[e] > 0.5f ? 1.f : 0.f;
@@ -67,78 +153,123 @@ __global__ void __launch_bounds__(kPrepThreads) unfold_grads_kernel(int n_levels
                                                                     const float *__restrict__ net_grad, const float *__restrict__ stats,
                                                                     float *__restrict__ small_grad) {
     __shared__ float s_red[32];
-    const int d_in = 3 + 2 * n_levels;
-    const int o_g0 = kH * d_in, o_b0 = o_g0 + kH, o_v1 = o_b0 + kH, o_g1 = o_v1 + kH, o_b1 = o_g1 + 1, o_var = o_b1 + 1;
+    const SmallLayout L(n_levels);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {   // lin0 row:  W = g v/|v|  ->  dg = <dW,v>/|v|,  dv = g/|v| (dW - <dW,v> v/|v|^2)
-        const int row = 2 * warp + q;
-        const float *v = small + row * d_in;
-        float ss = 0.f, dot = 0.f;
-        for (int i = lane; i < d_in; i += 32) {
-            float vi = v[i];
-            ss += vi * vi;
-            dot += net_grad[kOffW0T + i * kH + row] * vi;
-        }
-        ss = warp_sum_f(ss);
-        dot = warp_sum_f(dot);
-        float nrm = sqrtf(ss), g = small[o_g0 + row];
-        for (int i = lane; i < d_in; i += 32) small_grad[row * d_in + i] = g / nrm * (net_grad[kOffW0T + i * kH + row] - dot * v[i] / ss);
-        if (lane == 0) {
-            small_grad[o_g0 + row] = dot / nrm;
-            small_grad[o_b0 + row] = net_grad[kOffB0 + row];
-        }
-    }
-    float v1 = tid < kH ? small[o_v1 + tid] : 0.f, dw1 = tid < kH ? net_grad[kOffW1 + tid] : 0.f;
+    for (int q = 0; q < 2; ++q) unfold_row(L, 2 * warp + q, lane, small, net_grad, small_grad);
+    float v1 = tid < kH ? small[L.v1 + tid] : 0.f, dw1 = tid < kH ? net_grad[kOffW1 + tid] : 0.f;
     float ss1 = block_sum(v1 * v1, s_red);
     float dot1 = block_sum(dw1 * v1, s_red);
-    float n1 = sqrtf(ss1), g1 = small[o_g1];
-    if (tid < kH) small_grad[o_v1 + tid] = g1 / n1 * (dw1 - dot1 * v1 / ss1);
-    if (tid == 0) {
-        small_grad[o_g1] = dot1 / n1;
-        small_grad[o_b1] = net_grad[kOffB1];
-        float e = expf(small[o_var] * 10.f);
-        small_grad[o_var] = (e >= 1e-6f && e <= 1e6f) ? stats[4] * 10.f * e : 0.f;
+    unfold_tail(L, tid, ss1, dot1, small, net_grad, stats[4], small_grad);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(int64_t n, float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
+                                                   float *__restrict__ v, __half *__restrict__ p16, int64_t f16_start, AdamCoef c) {
+    const int64_t n4 = n >> 2;
+    adam_sweep4(c, 0, n4, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, p, g, m, v, p16, f16_start);
+    // tail (n not a multiple of 4)
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_elem(c, pi, g[i], mi, vi);
+        p[i] = pi;
+        m[i] = mi;
+        v[i] = vi;
+        g[i] = 0.f;
+        if (p16 && i >= f16_start) p16[i - f16_start] = __float2half_rn(pi);
     }
 }
 
-// torch.optim.Adam (no amsgrad / weight decay): p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-__global__ void __launch_bounds__(256) adam_kernel(int64_t n, float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
-                                                   float *__restrict__ v, __half *__restrict__ p16, int64_t f16_start, float lr,
-                                                   float b1, float b2, float eps, float bc1, float rsqrt_bc2, float gscale) {
-    const int64_t n4 = n >> 2;
-    const float step = lr / bc1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        float4 P = reinterpret_cast<float4 *>(p)[i], G = reinterpret_cast<float4 *>(g)[i];
-        float4 M = reinterpret_cast<float4 *>(m)[i], V = reinterpret_cast<float4 *>(v)[i];
-        float *pp = &P.x, *gg = &G.x, *mm = &M.x, *vv = &V.x;
+// ---- step tail: everything between the backward of iteration `it` and the marcher of iteration `it + 1` in ONE launch ----
+//   block 0                 weight-norm backward (net_grad -> small_grad), Adam on the MLP / variance block, weight-norm fold of the
+//                           UPDATED parameters into `net` for the next forward, net_grad zeroed -- all through shared memory
+//   blocks 1 .. n_sampler   device patch sampler for iteration it + 1 (independent of the parameters)
+//   remaining blocks        Adam over the live hash-table levels + gradient zeroing + fp16 table refresh
+// Replaces unfold_grads (1 CTA) -> adam -> prep_net (1 CTA) -> sample_patches: three serial single-CTA latency chains and a
+// launch overlap with the HBM sweep instead of preceding / following it.
+struct TailArgs {
+    AdamCoef coef;
+    float *p, *g, *m, *v;
+    __half *p16;
+    int64_t small_pad, n_live;   // floats; n_live = live table floats (multiple of 4)
+    int n_levels, do_unfold;
+    float *net, *net_grad;
+    const float *stats;
+    int n_sampler_blocks, n_patches;
+    uint64_t seed, step;
+    snb_dataset ds;
+    snb_batch_out out;
+};
+constexpr int kTailThreads = 1024;
+constexpr int kSmallMax = kH * kDinMax + 3 * kH + 3;   // 2435
+constexpr int kSmallIters = (kSmallMax + kTailThreads - 1) / kTailThreads;   // 3
+
+__global__ void __launch_bounds__(kTailThreads) train_tail_kernel(const __grid_constant__ TailArgs a) {
+    if (blockIdx.x > (unsigned)a.n_sampler_blocks) {   // ---- table Adam ----
+        const int64_t nb = gridDim.x - 1 - a.n_sampler_blocks, b = blockIdx.x - 1 - a.n_sampler_blocks;
+        const int64_t i0 = a.small_pad >> 2;
+        adam_sweep4(a.coef, i0, i0 + (a.n_live >> 2), b * kTailThreads + threadIdx.x, nb * kTailThreads, a.p, a.g, a.m, a.v, a.p16,
+                    a.small_pad);
+        return;
+    }
+    if (blockIdx.x >= 1) {   // ---- sampler for the next iteration ----
+        sample_patch_ray(a.ds, a.n_patches, a.seed, a.step, a.out, (blockIdx.x - 1) * kTailThreads + threadIdx.x);
+        return;
+    }
+    // ---- block 0: MLP / variance block.  One global round trip: every load is issued before the first use. ----
+    __shared__ float s_p[kSmallIters * kTailThreads], s_g[kSmallIters * kTailThreads], s_ng[kSmallIters * kTailThreads];
+    __shared__ float s_norm[kH], s_red[4];
+    const SmallLayout L(a.n_levels);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float pr[kSmallIters], mr[kSmallIters], vr[kSmallIters], xr[kSmallIters];   // xr: net_grad (to unfold) or the unfolded gradient
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            float gr = gg[a] * gscale;
-            mm[a] = b1 * mm[a] + (1.f - b1) * gr;
-            vv[a] = b2 * vv[a] + (1.f - b2) * gr * gr;
-            pp[a] -= step * mm[a] / (sqrtf(vv[a]) * rsqrt_bc2 + eps);
-        }
-        reinterpret_cast<float4 *>(p)[i] = P;
-        reinterpret_cast<float4 *>(m)[i] = M;
-        reinterpret_cast<float4 *>(v)[i] = V;
-        reinterpret_cast<float4 *>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p16 && 4 * i >= f16_start) {   // fp16 copy of the parameters from f16_start on (the hash table behind the MLP block)
-            __half2 *q = reinterpret_cast<__half2 *>(p16 + (4 * i - f16_start));
-            q[0] = __floats2half2_rn(P.x, P.y);
-            q[1] = __floats2half2_rn(P.z, P.w);
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        const bool in = e < L.n;
+        pr[k] = in ? a.p[e] : 0.f;
+        mr[k] = in ? a.m[e] : 0.f;
+        vr[k] = in ? a.v[e] : 0.f;
+        xr[k] = a.do_unfold ? (e < kNetFloats ? a.net_grad[e] : 0.f) : (in ? a.g[e] : 0.f);
+    }
+    const float d_inv_s = a.do_unfold ? a.stats[4] : 0.f;
+#pragma unroll
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        s_p[e] = pr[k];
+        (a.do_unfold ? s_ng : s_g)[e] = xr[k];
+    }
+    __syncthreads();
+    for (int e = tid; e < kNetFloats; e += kTailThreads) a.net_grad[e] = 0.f;   // ready for the next backward
+    if (a.do_unfold) {
+        for (int row = warp; row < kH; row += kTailThreads / 32) unfold_row(L, row, lane, s_p, s_ng, s_g);
+        float v1 = tid < kH ? s_p[L.v1 + tid] : 0.f, dw1 = tid < kH ? s_ng[kOffW1 + tid] : 0.f;
+        float ss1 = warp_sum_f(v1 * v1), dot1 = warp_sum_f(dw1 * v1);
+        if (warp < 2 && lane == 0) { s_red[warp] = ss1; s_red[2 + warp] = dot1; }
+        __syncthreads();
+        unfold_tail(L, tid, s_red[0] + s_red[1], s_red[2] + s_red[3], s_p, s_ng, d_inv_s, s_g);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        if (e < L.n) {
+            adam_elem(a.coef, pr[k], s_g[e], mr[k], vr[k]);
+            s_p[e] = pr[k];
+            a.p[e] = pr[k];
+            a.m[e] = mr[k];
+            a.v[e] = vr[k];
+            a.g[e] = 0.f;
         }
     }
-    // tail (n not a multiple of 4)
-    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float gr = g[i] * gscale;
-        float mi = b1 * m[i] + (1.f - b1) * gr, vi = b2 * v[i] + (1.f - b2) * gr * gr;
-        m[i] = mi;
-        v[i] = vi;
-        p[i] -= step * mi / (sqrtf(vi) * rsqrt_bc2 + eps);
-        g[i] = 0.f;
-        if (p16 && i >= f16_start) p16[i - f16_start] = __float2half_rn(p[i]);
+    __syncthreads();
+    for (int row = warp; row < kH; row += kTailThreads / 32) {
+        float ss = row_sumsq(s_p + row * L.d_in, L.d_in, lane);
+        if (lane == 0) s_norm[row] = sqrtf(ss);
     }
+    float v1n = tid < kH ? s_p[L.v1 + tid] : 0.f;
+    float ssn = warp_sum_f(v1n * v1n);
+    if (warp < 2 && lane == 0) s_red[warp] = ssn;
+    __syncthreads();
+    fold_store(L, s_p, s_norm, sqrtf(s_red[0] + s_red[1]), a.net, tid, kTailThreads);
 }
 
 }  // namespace snb
@@ -174,8 +305,8 @@ int32_t adam_launch(int64_t n, float *param, float *grad, float *exp_avg, float 
     double bc1 = 1.0 - pow((double)beta1, step_count), bc2 = 1.0 - pow((double)beta2, step_count);
     int64_t blocks = cdiv(n / 4 + 1, 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    adam_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(n, param, grad, exp_avg, exp_avg_sq, (__half *)param_f16, f16_start, lr, beta1, beta2,
-                                                        eps, (float)bc1, (float)(1.0 / sqrt(bc2)), grad_scale);
+    const AdamCoef coef{beta1, beta2, eps, lr / (float)bc1, (float)(1.0 / sqrt(bc2)), grad_scale};
+    adam_kernel<<<(unsigned)blocks, 256, 0, S(stream)>>>(n, param, grad, exp_avg, exp_avg_sq, (__half *)param_f16, f16_start, coef);
     SNB_LAUNCH_CHECK("adam_step");
     return SNB_OK;
 }
@@ -184,4 +315,49 @@ int32_t adam_launch(int64_t n, float *param, float *grad, float *exp_avg, float 
 extern "C" int32_t snb_adam_step(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *param_f16, float lr,
                                  float beta1, float beta2, float eps, int32_t step_count, float grad_scale, snb_stream_t stream) {
     return snb::adam_launch(n, param, grad, exp_avg, exp_avg_sq, param_f16, 0, lr, beta1, beta2, eps, step_count, grad_scale, stream);
+}
+
+extern "C" int32_t snb_train_tail(const snb_train_ctx *c, float lr, int32_t step_count, float grad_scale, int32_t grads_unfolded,
+                                  const snb_dataset *ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,
+                                  const snb_batch_out *out_next, snb_stream_t stream) {
+    SNB_REQUIRE(c, SNB_ERR_NULL, "train_tail: null ctx");
+    SNB_REQUIRE(c->flat_param && c->flat_grad && c->exp_avg && c->exp_avg_sq && c->net_grad && c->stats && c->net.net && c->net.table_f16,
+                SNB_ERR_NULL, "train_tail: null buffer");
+    SNB_REQUIRE(step_count >= 1 && c->n_levels >= 1 && c->n_levels <= SNB_MAX_LEVELS && c->net.n_active <= (uint32_t)c->n_levels, SNB_ERR_ARG,
+                "train_tail: bad step_count / level counts");
+    SNB_REQUIRE(c->small_pad % 4 == 0 && c->small_pad >= kSmallMax, SNB_ERR_ARG, "train_tail: small_pad must be a multiple of 4 and >= 2435");
+    SNB_REQUIRE(aligned(c->flat_param, 16) && aligned(c->flat_grad, 16) && aligned(c->exp_avg, 16) && aligned(c->exp_avg_sq, 16) &&
+                    aligned(c->net.table_f16, 8), SNB_ERR_ALIGN, "train_tail: buffers must be 16-byte aligned");
+    TailArgs a{};
+    const float beta1 = 0.9f, beta2 = 0.999f;   // bias corrections from the fp32 betas, like snb_adam_step / adam_launch
+    const double bc1 = 1.0 - pow((double)beta1, step_count), bc2 = 1.0 - pow((double)beta2, step_count);
+    a.coef = AdamCoef{beta1, beta2, 1e-8f, lr / (float)bc1, (float)(1.0 / sqrt(bc2)), grad_scale};
+    a.p = c->flat_param; a.g = c->flat_grad; a.m = c->exp_avg; a.v = c->exp_avg_sq;
+    a.p16 = (__half *)const_cast<void *>(c->net.table_f16);
+    a.small_pad = c->small_pad;
+    a.n_live = 2 * (int64_t)c->net.meta.offsets[c->net.n_active];   // levels >= n_active: zero gradient and state, skipping is exact
+    a.n_levels = c->n_levels;
+    a.do_unfold = grads_unfolded ? 0 : 1;
+    a.net = const_cast<float *>(c->net.net);
+    a.net_grad = c->net_grad;
+    a.stats = c->stats;
+    if (ds_next && n_patches_next > 0) {
+        SNB_REQUIRE(out_next, SNB_ERR_NULL, "train_tail: null sampler output");
+        SNB_REQUIRE(ds_next->W > 3 && ds_next->H > 3 && ds_next->n_train > 0 && ds_next->n_images > 0, SNB_ERR_ARG, "train_tail: bad dataset sizes");
+        SNB_REQUIRE(ds_next->normals && ds_next->masks && ds_next->intrinsics_inv && ds_next->pose && ds_next->v_inverse && ds_next->train_ids,
+                    SNB_ERR_NULL, "train_tail: null dataset tensor");
+        SNB_REQUIRE(out_next->rays_o && out_next->rays_d && out_next->plane_n && out_next->near_ && out_next->far_ && out_next->v_inv &&
+                        out_next->normal_gt && out_next->mask, SNB_ERR_NULL, "train_tail: null sampler output tensor");
+        a.ds = *ds_next;
+        a.out = *out_next;
+        a.n_patches = n_patches_next;
+        a.seed = seed;
+        a.step = next_step;
+        a.n_sampler_blocks = (int)cdiv((int64_t)n_patches_next * SNB_PATCH, kTailThreads);
+    }
+    int64_t adam_blocks = cdiv(a.n_live / 4, kTailThreads);
+    if (adam_blocks > kNumSMs * 2) adam_blocks = kNumSMs * 2;
+    train_tail_kernel<<<(unsigned)(1 + a.n_sampler_blocks + adam_blocks), kTailThreads, 0, S(stream)>>>(a);
+    SNB_LAUNCH_CHECK("train_tail");
+    return SNB_OK;
 }

@@ -1,68 +1,15 @@
 // sampler.cu -- device-side random patch sampler (models/dataset_loader.py:223-297) and the single-call
 // training step that enqueues the whole iteration from C++ (no per-kernel Python dispatch).
-#include "sdf_core.cuh"
+#include "sampler.cuh"
 
 namespace snb {
 
 int32_t adam_launch(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *param_f16, int64_t f16_start, float lr,
                     float beta1, float beta2, float eps, int32_t step_count, float grad_scale, snb_stream_t stream);
 
-// Philox4x32-10 (Salmon et al. 2011), counter-based: ctr = (step lo, step hi, index, stream), key = seed
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u;
-        key.y += 0xBB67AE85u;
-    }
-    return ctr;
-}
-__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }  // [0,1), 24 bits like torch.rand
-
 __global__ void __launch_bounds__(256) sample_patches_kernel(snb_dataset ds, int n_patches, uint64_t seed, uint64_t step,
                                                              snb_batch_out out) {
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n_patches * SNB_PATCH) return;
-    int i = tid / SNB_PATCH, k = tid % SNB_PATCH;
-    uint4 r = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)i, 0x5a4dce11u),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    int cx = 1 + (int)(r.x % (uint32_t)(ds.W - 3));   // randint(low=1, high=W-2)
-    int cy = 1 + (int)(r.y % (uint32_t)(ds.H - 3));
-    int view = __ldg(ds.train_ids + (r.z % (uint32_t)ds.n_train));
-    int px = cx + (k % 3) - 1, py = cy + (k / 3) - 1;
-    const float *Ki = ds.intrinsics_inv + view * 16, *Pm = ds.pose + view * 16;
-    float fx = (float)px, fy = (float)py;
-    float p[3], d[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = __ldg(Ki + 4 * a) * fx + __ldg(Ki + 4 * a + 1) * fy + __ldg(Ki + 4 * a + 2);
-    float inv = 1.f / sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-    p[0] *= inv; p[1] *= inv; p[2] *= inv;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) d[a] = __ldg(Pm + 4 * a) * p[0] + __ldg(Pm + 4 * a + 1) * p[1] + __ldg(Pm + 4 * a + 2) * p[2];
-    float o[3] = {__ldg(Pm + 3), __ldg(Pm + 7), __ldg(Pm + 11)};
-    int64_t rk = (int64_t)i * SNB_PATCH + k;
-    out.rays_d[3 * rk] = d[0]; out.rays_d[3 * rk + 1] = d[1]; out.rays_d[3 * rk + 2] = d[2];
-    int64_t pix = ((int64_t)view * ds.H + py) * ds.W + px;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) out.normal_gt[3 * rk + a] = __ldg(ds.normals + 3 * pix + a);
-    out.mask[rk] = __ldg(ds.masks + pix);
-#pragma unroll
-    for (int a = 0; a < 9; ++a) out.v_inv[9 * rk + a] = __ldg(ds.v_inverse + 9 * pix + a);
-    if (k == SNB_PATCH / 2) {
-        out.rays_o[3 * i] = o[0]; out.rays_o[3 * i + 1] = o[1]; out.rays_o[3 * i + 2] = o[2];
-        out.plane_n[3 * i] = __ldg(Pm + 2); out.plane_n[3 * i + 1] = __ldg(Pm + 6); out.plane_n[3 * i + 2] = __ldg(Pm + 10);
-        // near_far_from_sphere, models/dataset_loader.py:279-297
-        float a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-        float b = 2.0f * (o[0] * d[0] + o[1] * d[1] + o[2] * d[2]);
-        float c = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] - 1.0f;
-        float mid = 0.5f * (-b) / a;
-        float root = sqrtf(b * b - 4.f * a * c) / (2.f * a);  // NaN if the ray misses the unit sphere
-        out.near_[i] = mid - root;
-        out.far_[i] = mid + root;
-        if (out.jitter) out.jitter[i] = u01(r.w);
-    }
+    sample_patch_ray(ds, n_patches, seed, step, out, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ---- fused occupancy update --------------------------------------------------------------------
@@ -186,6 +133,24 @@ extern "C" int32_t snb_train_fwd_bwd(const snb_train_ctx *c, float step_size, fl
     if ((rc = snb_sdf_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad, stream)))
         return rc;
     return snb_unfold_grads(c->n_levels, c->flat_param, c->net_grad, c->stats, c->flat_grad, stream);
+}
+
+// The lean iteration: `net` already holds the folded weights of the current parameters and net_grad is zero (both left
+// behind by snb_train_tail of the previous iteration), so no prep_net / memset / unfold_grads launches.
+extern "C" int32_t snb_train_fwd_bwd_lean(const snb_train_ctx *c, float step_size, float early_stop_eps, float normal_weight, float mask_weight,
+                                          float eikonal_weight, snb_stream_t stream) {
+    SNB_REQUIRE(c, SNB_ERR_NULL, "train_fwd_bwd_lean: null ctx");
+    SNB_REQUIRE(c->flat_param && c->flat_grad && c->net_grad && c->stats && c->sdf && c->feats && c->d_sdf0 && c->d_sdf1 && c->comp && c->wsum,
+                SNB_ERR_NULL, "train_fwd_bwd_lean: null buffer");
+    const int n = c->batch.n_patches;
+    int32_t rc;
+    if ((rc = snb_march_visible(&c->batch, &c->net, c->roi, c->res_x, c->res_y, c->res_z, c->grid_binary, step_size, c->jitter, early_stop_eps,
+                                &c->samples, stream))) return rc;
+    if ((rc = snb_compact_samples_stats(n, &c->samples, n * SNB_PATCH, c->batch.mask, c->stats, stream))) return rc;
+    if ((rc = snb_sdf_fwd_patch(&c->batch, &c->net, &c->samples, c->sdf, c->feats, stream))) return rc;
+    if ((rc = snb_render_fused(&c->batch, &c->net, &c->samples, c->sdf, normal_weight, mask_weight, eikonal_weight, c->comp, c->wsum, c->d_sdf0,
+                               c->d_sdf1, c->stats, stream))) return rc;
+    return snb_sdf_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad, stream);
 }
 
 extern "C" int32_t snb_train_optim(const snb_train_ctx *c, float lr, int32_t step_count, float grad_scale, snb_stream_t stream) {

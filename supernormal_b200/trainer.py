@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -103,6 +104,7 @@ class SDFModel:
         self.net = torch.zeros(NET_FLOATS, device=self.device)
         self.net_grad = torch.zeros(NET_FLOATS, device=self.device)
         self.n_active = 0  # SDFNetwork.bindwidth
+        self.net_stale = True  # `net` / `net_grad` are not (folded current parameters / zero): the lean step calls prep() first
         self.refresh_table_f16()
 
     def _small_offsets(self) -> Dict[str, int]:
@@ -178,6 +180,7 @@ class SDFModel:
         s[o["b1"]] = f["lin1.bias"].flatten()[0]
         s[o["var"]] = sd["variance_network_fine"]["variance"].to(self.device).float()
         self.refresh_table_f16()
+        self.net_stale = True
 
 
 class SampleBuffers:
@@ -341,23 +344,27 @@ class FusedTrainer:
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
         self.seed = dp.rank_seed(seed, rank)   # every rank draws its own patches (weak scaling)
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
+        self.lean = os.environ.get("SNB_LEAN", "1") != "0"   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
+                                      # (snb_train_tail) unfolds, runs Adam, folds the updated weights and pre-samples the next batch
         self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
         self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
         dv = self.device
         n, Pn = self.n_patches, P
-        self.own_batch = dict(rays_o=torch.zeros(n, 3, device=dv), rays_d=torch.zeros(n, Pn, 3, device=dv), plane_n=torch.zeros(n, 3, device=dv),
-                              near=torch.zeros(n, device=dv), far=torch.zeros(n, device=dv), v_inv=torch.zeros(n, Pn, 9, device=dv),
-                              normal_gt=torch.zeros(n, Pn, 3, device=dv), mask=torch.zeros(n, Pn, device=dv))
-        self.own_jitter = torch.zeros(n, device=dv)
+        # two batch slots: the tail kernel of iteration `it` writes the batch of `it + 1` into the slot iteration `it` is not using
+        self._own = [dict(rays_o=torch.zeros(n, 3, device=dv), rays_d=torch.zeros(n, Pn, 3, device=dv), plane_n=torch.zeros(n, 3, device=dv),
+                          near=torch.zeros(n, device=dv), far=torch.zeros(n, device=dv), v_inv=torch.zeros(n, Pn, 9, device=dv),
+                          normal_gt=torch.zeros(n, Pn, 3, device=dv), mask=torch.zeros(n, Pn, device=dv)) for _ in range(2)]
+        self._own_jitter = [torch.zeros(n, device=dv) for _ in range(2)]
+        self._slot = 0                 # slot of the batch sample_batch_device() last handed out
+        self._presampled = (-1, 0)     # (iteration, slot) filled ahead by the tail kernel
         self.train_ids = torch.tensor(dataset.train_images, dtype=torch.int32, device=dv)
         # the C ABI reads dense fp32 tensors (torch.inverse may hand back column-major batches)
         self._ds_tensors = [t.to(dv, torch.float32).contiguous() for t in (dataset.normals, dataset.masks, dataset.intrinsics_all_inv,
                                                                             dataset.pose_all, dataset.V_inverse_all)]
         self.ds_struct = SnbDataset(dataset.n_images, dataset.H, dataset.W, len(dataset.train_images),
                                     *[t.data_ptr() for t in self._ds_tensors], self.train_ids.data_ptr())
-        ob = self.own_batch
-        self.out_struct = SnbBatchOut(*[ob[k].data_ptr() for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")],
-                                      self.own_jitter.data_ptr())
+        self._out_structs = [SnbBatchOut(*[ob[k].data_ptr() for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")],
+                                         jit.data_ptr()) for ob, jit in zip(self._own, self._own_jitter)]
         self.occs_prev = torch.zeros(self.grid.num_cells, device=dv)
         self.occ_ws = torch.zeros(2, dtype=torch.float64, device=dv)
         self.iter_step = 0
@@ -365,6 +372,15 @@ class FusedTrainer:
         self.gen = torch.Generator(device=self.device).manual_seed(seed + rank)
         self.np_rng = np.random.RandomState(seed + rank)
         self.last_batch = None
+
+    @property
+    def own_batch(self) -> Dict[str, torch.Tensor]:
+        """The device-sampled batch of the current / last iteration."""
+        return self._own[self._slot]
+
+    @property
+    def own_jitter(self) -> torch.Tensor:
+        return self._own_jitter[self._slot]
 
     # -- schedule pieces -----------------------------------------------------------------------
     def step_size(self, it: int) -> float:
@@ -379,7 +395,8 @@ class FusedTrainer:
 
     def update_occupancy(self, it: int):
         rm = self.conf["ray_marching"]
-        self.model.prep()
+        if not self.lean or self.model.net_stale:   # the lean step keeps `net` folded (snb_train_tail)
+            self.model.prep()
         if self.fused_host:
             net = self.model.net_struct()
             binary = self.grid._binary
@@ -390,8 +407,13 @@ class FusedTrainer:
             self.grid._update(step=it, occ_eval_fn=lambda x: self.model.sdf(x, mode=1), occ_thre=rm["occ_threshold"])
 
     def sample_batch_device(self, it: int):
-        """Device-side sampler: fills self.own_batch / self.own_jitter in one launch."""
-        call("snb_sample_patches", C.byref(self.ds_struct), self.n_patches, self.seed, it, C.byref(self.out_struct))
+        """Device-side sampler: self.own_batch / self.own_jitter for iteration `it` -- the slot the previous iteration's tail
+        kernel already filled, or one launch now.  Counter-based RNG keyed by (seed, it): the batch is the same either way."""
+        if self._presampled[0] == it:
+            self._slot = self._presampled[1]
+        else:
+            call("snb_sample_patches", C.byref(self.ds_struct), self.n_patches, self.seed, it, C.byref(self._out_structs[self._slot]))
+        self._presampled = (-1, 0)
         return self.own_batch, self.own_jitter
 
     def _ctx(self, batch: dict, jitter) -> SnbTrainCtx:
@@ -414,25 +436,37 @@ class FusedTrainer:
                     far=far.contiguous(), v_inv=vinv.view(-1, P, 9), normal_gt=nrm.view(-1, P, 3), mask=msk.view(-1, P).contiguous())
 
     # -- one iteration ---------------------------------------------------------------------------
-    def forward_backward(self, batch: dict, step_size: float, jitter: Optional[torch.Tensor]):
-        """march -> sdf -> render -> loss -> backward; leaves gradients in model.grad (small + table)."""
+    def forward_backward(self, batch: dict, step_size: float, jitter: Optional[torch.Tensor], lean: bool = False):
+        """march -> sdf -> render -> loss -> backward; leaves gradients in model.grad (small + table).
+        lean=True (what train_step uses): `net` is already folded and net_grad zero (left by the previous tail kernel), the
+        loss accumulators are reset by the compaction kernel, and the MLP gradient stays in model.net_grad w.r.t. the FOLDED
+        weights -- optimizer_step's tail kernel unfolds it."""
         m, b = self.model, self.buf
         c = self.conf
         self.last_batch = batch
+        self._grads_folded = lean
+        if lean and m.net_stale:
+            m.prep()
+            m.net_grad.zero_()
+            m.net_stale = False
         if self.fused_host:
             ctx = self._ctx(batch, jitter)
-            call("snb_train_fwd_bwd", C.byref(ctx), float(step_size), 1e-8, float(c["normal_weight"]), float(c["mask_weight"]),
-                 float(c["eikonal_weight"]))
+            call("snb_train_fwd_bwd_lean" if lean else "snb_train_fwd_bwd", C.byref(ctx), float(step_size), 1e-8, float(c["normal_weight"]),
+                 float(c["mask_weight"]), float(c["eikonal_weight"]))
             return
         bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"],
                                batch["v_inv"], batch["normal_gt"], batch["mask"])
-        m.prep(batch["mask"], b.stats)
+        if not lean:
+            m.prep(batch["mask"], b.stats)
         net = m.net_struct()
         rb, rn, rs = C.byref(bs), C.byref(net), C.byref(b.struct)
         res = self.grid._res
         grid_u8 = self.grid.binary.view(torch.uint8)
         call("snb_march_visible", rb, rn, ptr(self.grid.roi_aabb), *res, ptr(grid_u8), float(step_size), ptr(jitter), 1e-8, rs)
-        call("snb_compact_samples", self.n_patches, rs)
+        if lean:
+            call("snb_compact_samples_stats", self.n_patches, rs, batch["mask"].numel(), ptr(batch["mask"]), ptr(b.stats))
+        else:
+            call("snb_compact_samples", self.n_patches, rs)
         call("snb_sdf_fwd_patch", rb, rn, rs, ptr(b.sdf), ptr(b.feats))
         if self.legacy_render:   # the three serial-chain kernels the single-launch render stage replaced (kept for cross-checks)
             call("snb_render_fwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), None, None, ptr(b.stats))
@@ -443,17 +477,38 @@ class FusedTrainer:
         else:
             call("snb_render_fused", rb, rn, rs, ptr(b.sdf), float(c["normal_weight"]), float(c["mask_weight"]), float(c["eikonal_weight"]),
                  ptr(b.comp), ptr(b.wsum), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
-        m.net_grad.zero_()
+        if not lean:
+            m.net_grad.zero_()
         call("snb_sdf_bwd_patch", rb, rn, rs, ptr(b.feats), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
-        call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(b.stats), ptr(m.grad))
+        if not lean:
+            call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(b.stats), ptr(m.grad))
 
-    def optimizer_step(self):
+    def optimizer_step(self, presample_next: bool = False):
+        """Adam (exp_runner.py:205-207).  After a lean forward_backward: ONE launch (snb_train_tail) that also unfolds the MLP
+        gradient, folds the updated weights for the next forward and, with presample_next, draws the next iteration's batch."""
         m = self.model
         n_live = dp.live_numel(SMALL_PAD, m.offsets, m.n_active)  # zero-gradient levels are exact no-ops for Adam without weight decay
-        gscale = dp.allreduce_live_gradients(m.grad, n_live, self.world_size)
         t = self.iter_step + 1
         ctx = self._ctx(self.last_batch, None)
-        call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)   # one Adam sweep: MLP block + live table levels + fp16 refresh
+        if not getattr(self, "_grads_folded", False):
+            gscale = dp.allreduce_live_gradients(m.grad, n_live, self.world_size)
+            call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)   # one Adam sweep: MLP block + live table levels + fp16 refresh
+            m.net_stale = True
+            return
+        unfolded = 0
+        gscale = 1.0
+        if self.world_size > 1:   # the allreduce works on (v, g, b, variance) gradients: unfold first, tail skips its unfold
+            call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(self.buf.stats), ptr(m.grad))
+            gscale = dp.allreduce_live_gradients(m.grad, n_live, self.world_size)
+            unfolded = 1
+        if presample_next:
+            nxt = 1 - self._slot
+            call("snb_train_tail", C.byref(ctx), float(self.lr), t, gscale, unfolded, C.byref(self.ds_struct), self.n_patches, self.seed,
+                 self.iter_step + 1, C.byref(self._out_structs[nxt]))
+            self._presampled = (self.iter_step + 1, nxt)
+        else:
+            call("snb_train_tail", C.byref(ctx), float(self.lr), t, gscale, unfolded, None, 0, 0, 0, None)
+        self._grads_folded = False
 
     def train_step(self, batch: Optional[dict] = None, jitter: Optional[torch.Tensor] = None):
         c, rm = self.conf, self.conf["ray_marching"]
@@ -462,14 +517,15 @@ class FusedTrainer:
             self.update_occupancy(it)
         if it % c["increase_bindwidth_every"] == 0:
             self.model.n_active = min(self.model.n_active + 1, self.model.n_levels)
-        if batch is None and self.device_sampler:
+        own = batch is None and self.device_sampler
+        if own:
             batch, jitter = self.sample_batch_device(it)
         if batch is None:
             batch = self.sample_batch()
         if jitter is None:
             jitter = torch.rand(self.n_patches, device=self.device, generator=self.gen)
-        self.forward_backward(batch, self.step_size(it), jitter)
-        self.optimizer_step()
+        self.forward_backward(batch, self.step_size(it), jitter, lean=self.lean)
+        self.optimizer_step(presample_next=own and self.lean)
         self.iter_step += 1
         self.lr = self.conf["learning_rate"] * self._lr_factor()
 
@@ -499,7 +555,7 @@ class FusedTrainer:
             return M * (4 + 4 * na) + S * 12
         if name == "snb_sdf_bwd_patch":      # read kept features (4 B/level) + positions' inputs + seeds (d_sdf0, d_sdf1); the table-gradient
             return M * (4 * na + 4) + 2 * P * S * 4   # reductions are L2 traffic (l2_bytes), SURVEY.md §8d
-        if name == "snb_train_optim":         # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
+        if name in ("snb_train_optim", "snb_train_tail"):   # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
             return (SMALL_PAD + 2 * m.offsets[na]) * (16 + 16) + 2 * m.offsets[na] * 2
         if name == "snb_march_visible":      # 40 B in per ray + 8 B per emitted sample (scratch)
             return self.n_patches * 40 + S * 8

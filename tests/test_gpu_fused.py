@@ -426,3 +426,141 @@ def test_fma_backward_cross_check(cuda):
                         "test_fused_forward_backward_vs_oracle and (0.3-False-2 or 0.3-False-6)"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-2000:]
+
+
+def test_train_tail_bit_identical_to_separate_kernels(cuda):
+    """snb_train_tail -- weight-norm backward, Adam (MLP block + live table levels + fp16 refresh), fold of the updated weights,
+    net_grad reset and the next batch, ONE launch -- against snb_unfold_grads -> snb_train_optim -> snb_prep_net ->
+    snb_sample_patches on the same state: every buffer bit-identical, with and without pre-unfolded gradients."""
+    import ctypes as C
+    from supernormal_b200._lib import call, ptr
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    tr = FusedTrainer(ds, dict(DILIGENT_CONF, batch_size=300, end_iter=200, increase_bindwidth_every=1), device=cuda)
+    for _ in range(5):   # non-trivial parameters and Adam state, 5 live levels
+        tr.train_step()
+    m = tr.model
+    batch, jitter = tr.sample_batch_device(5)
+    tr.forward_backward(batch, tr.step_size(5), jitter, lean=True)   # gradient w.r.t. the folded weights in net_grad, table gradient in grad
+    names = ("flat", "grad", "exp_avg", "exp_avg_sq", "table_f16", "net", "net_grad")
+    snap = {k: getattr(m, k).clone() for k in names}
+    stats = tr.buf.stats.clone()
+    assert snap["net_grad"].abs().sum() > 0 and snap["grad"].abs().sum() > 0 and stats[4] != 0
+    t, lr = 6, 3e-4
+    nxt = 1 - tr._slot
+
+    def restore():
+        for k in names:
+            getattr(m, k).copy_(snap[k])
+        tr.buf.stats.copy_(stats)
+        for v in tr._own[nxt].values():
+            v.fill_(-7.0)
+
+    def result():
+        torch.cuda.synchronize()
+        return {**{k: getattr(m, k).clone() for k in names}, **{"b_" + k: v.clone() for k, v in tr._own[nxt].items()},
+                "jit": tr._own_jitter[nxt].clone()}
+
+    restore()
+    ctx = tr._ctx(batch, None)
+    call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(tr.buf.stats), ptr(m.grad))
+    call("snb_train_optim", C.byref(ctx), lr, t, 1.0)
+    m.prep()
+    m.net_grad.zero_()
+    call("snb_sample_patches", C.byref(tr.ds_struct), tr.n_patches, tr.seed, 6, C.byref(tr._out_structs[nxt]))
+    ref = result()
+    assert not torch.equal(ref["flat"], snap["flat"]) and not torch.equal(ref["net"], snap["net"])
+
+    restore()
+    call("snb_train_tail", C.byref(ctx), lr, t, 1.0, 0, C.byref(tr.ds_struct), tr.n_patches, tr.seed, 6, C.byref(tr._out_structs[nxt]))
+    got = result()
+    for k in ref:   # near/far are NaN for rays that miss the unit sphere
+        same = torch.equal(torch.nan_to_num(got[k].float(), nan=-123.0), torch.nan_to_num(ref[k].float(), nan=-123.0))
+        assert same, (k, (got[k].float() - ref[k].float()).abs().max().item())
+    assert (got["grad"] == 0).all() and (got["net_grad"] == 0).all()
+
+    restore()   # data-parallel order: unfold -> (allreduce) -> tail with grads_unfolded = 1, no sampler blocks
+    call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(tr.buf.stats), ptr(m.grad))
+    call("snb_train_tail", C.byref(ctx), lr, t, 1.0, 1, None, 0, 0, 0, None)
+    got = result()
+    for k in names:
+        assert torch.equal(got[k], ref[k]), k
+    assert all((v == -7.0).all() for v in tr._own[nxt].values())
+
+
+def test_lean_step_equals_separate_launch_step(cuda):
+    """train_step with the lean launch sequence (marcher .. backward + ONE tail kernel that also pre-samples the next batch: 6
+    launches) against the same step with prep_net / unfold_grads / Adam / sample_patches as separate launches (lean=False)."""
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer
+    from supernormal_b200 import _lib
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    conf = dict(DILIGENT_CONF, batch_size=300, end_iter=200, increase_bindwidth_every=5)
+    a, b = FusedTrainer(ds, conf, device=cuda), FusedTrainer(ds, conf, device=cuda)
+    assert a.lean
+    b.lean = False
+    for it in range(12):
+        n0 = _lib.LAUNCH_COUNT
+        a.train_step()
+        if it % 8:   # no occupancy update in this iteration
+            assert _lib.LAUNCH_COUNT - n0 == 6   # marcher, compaction, SDF forward, render, SDF backward, tail
+        b.grid._binary.copy_(a.grid._binary)
+        b.grid.occs.copy_(a.grid.occs)
+        b.update_occupancy = lambda it: None
+        b.train_step()
+        for k in a.own_batch:   # pre-sampled by the previous tail kernel (a) vs sampled at the start of the step (b)
+            assert torch.equal(torch.nan_to_num(a.own_batch[k]), torch.nan_to_num(b.own_batch[k])), (it, k)
+        assert torch.equal(a.own_jitter, b.own_jitter)
+        if it == 0:   # identical inputs and parameters: identical forward; gradients differ by fp32 atomic order only
+            assert a.buf.totals.tolist() == b.buf.totals.tolist()
+            assert torch.equal(a.buf.stats[0], b.buf.stats[0])
+            assert torch.allclose(a.buf.stats[:4], b.buf.stats[:4], rtol=1e-5, atol=1e-7)
+            assert ((a.model.flat - b.model.flat).abs() > 1e-6).float().mean().item() < 1e-3
+            b.model.prep()   # a's tail kernel already folded the updated weights
+            assert torch.allclose(a.model.net, b.model.net, rtol=1e-4, atol=1e-6)
+        la, lb = a.loss_terms(), b.loss_terms()
+        assert abs(la["n_samples"] - lb["n_samples"]) <= 0.02 * la["n_samples"] + 5
+        assert abs(la["loss"] - lb["loss"]) <= 0.05 * abs(la["loss"]) + 1e-3
+    assert a.model.n_active == 3 and (a.model.net_grad == 0).all()
+
+
+@pytest.mark.parametrize("cap", [320, 4])
+def test_single_launch_compaction_equals_scan_then_compact(cuda, cap):
+    """snb_compact_samples_stats (per-CTA prefix sums + compaction + loss-accumulator reset, one launch) against
+    snb_compact_samples (single-CTA scan kernel, then compaction) on the same marcher output -- also when the sample lists
+    overflow their capacity (cap = 4 samples per ray) and have to be clipped."""
+    import ctypes as C
+    from supernormal_b200._lib import call, ptr
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer, make_batch_struct
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    tr = FusedTrainer(ds, dict(DILIGENT_CONF, batch_size=301), device=cuda, samples_per_ray_cap=cap)   # 301: ragged last CTA
+    tr.update_occupancy(0)
+    tr.model.n_active = 1
+    batch, jitter = tr.sample_batch_device(0)
+    b = tr.buf
+    bs = make_batch_struct(*[batch[k] for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")])
+    net = tr.model.net_struct()
+    rs = C.byref(b.struct)
+    call("snb_march_visible", C.byref(bs), C.byref(net), ptr(tr.grid.roi_aabb), *tr.grid._res, ptr(tr.grid.binary.view(torch.uint8)), 0.01,
+         ptr(jitter), 1e-8, rs)
+    outs = ("packed_info", "end_packed", "totals", "t0", "t1", "patch_idx", "end_slot", "slot_sample")
+    march_totals = b.totals.clone()
+
+    def run(name, *extra):
+        for k in outs:
+            getattr(b, k).fill_(-1)
+        b.totals.copy_(march_totals)
+        b.stats.fill_(3.0)
+        call(name, tr.n_patches, rs, *extra)
+        torch.cuda.synchronize()
+        return {k: getattr(b, k).clone() for k in outs}
+
+    ref = run("snb_compact_samples")
+    got = run("snb_compact_samples_stats", batch["mask"].numel(), ptr(batch["mask"]), ptr(b.stats))
+    S, E = ref["totals"][0].item(), ref["totals"][1].item()
+    assert S > 0 and E > 0 and (ref["totals"][2].item() == 1) == (cap == 4)
+    for k in outs:
+        assert torch.equal(got[k], ref[k]), k
+    assert b.stats[0].item() == pytest.approx((batch["mask"] > 0.5).sum().item() + 1e-5) and (b.stats[1:] == 0).all()
