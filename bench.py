@@ -92,7 +92,7 @@ class ClockSampler:
                 "samples": len(sm), "window": where}
 
 
-def cpu_port_run(steps, warmup, n_patches=64, threads=None):
+def cpu_port_run(steps, warmup, n_patches=64, threads=None, budget_s=None):
     """The oracle (PyTorch-CPU port of the reference operators) on a bounded sample of the workload."""
     from oracle import torch_ops as T
     from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
@@ -111,8 +111,13 @@ def cpu_port_run(steps, warmup, n_patches=64, threads=None):
     for _ in range(warmup):
         tr.step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done = 0
+    while done < steps:
         tr.step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:   # bounded sample: stop after the step that crosses the budget
+            break
+    steps = done
     dt = time.perf_counter() - t0
     return n_patches * 9 * steps / dt, dt / steps * 1e3, threads, f"{steps} steps of {n_patches} patches x 9 rays (of 2048) at the start of the schedule, analytic initial occupancy grid, no grid updates in the timed steps"
 
@@ -136,17 +141,42 @@ def ref_cuda_path_run(dev, warmup, steps, backend="reference"):
                     "same ATen/autograd step over the drop-in modules supernormal_b200.nerfacc_api + tcnn_api (no fused trainer)"}
 
 
+_STDOUT_FD = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner, warnings
+    of extensions) is sent to stderr; emit() writes the line to the real stdout."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 6)), max(1, min(args.warmup, 2))
-    v, ms, threads, sample = cpu_port_run(steps, warm)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+    # each step = a 64-patch sample of the 2048-patch batch (~1 s on 16 cores); K steps, or as many as fit into ~100 s of CPU work
+    warm = max(1, min(args.warmup, 3))
+    v, ms, threads, sample = cpu_port_run(max(1, args.steps), warm, budget_s=100.0)
+    steps = int(sample.split()[0])
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps,
+            "warmup": warm,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "reference has no CPU path (nerfacc/tcnn are CUDA-only); this is the PyTorch-CPU port of its operators (oracle/)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -164,6 +194,7 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args, rank)
     assert args.warmup >= 3, "timing rules: W >= 3"
@@ -315,7 +346,7 @@ def main():
         if world == 1 and not args.no_cpu:
             v, cms, threads, sample = cpu_port_run(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": cms}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
