@@ -332,6 +332,30 @@ int32_t snb_train_tail(const snb_train_ctx *h_ctx, float lr, int32_t step_count,
                        const snb_dataset *h_ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,
                        const snb_batch_out *h_out_next, snb_stream_t stream);
 
+/* Data-parallel step tail over NVLink peer memory (one process per GPU, one box): replaces
+ * snb_unfold_grads -> NCCL allreduce of the live gradient range -> snb_train_tail (exp_runner.py:205-207 under DDP-style
+ * data parallelism) by ONE kernel per rank.  All ranks' flat parameters / gradients / fp16 tables live in a symmetric,
+ * peer-mapped allocation (supernormal_b200/dp.py: PeerGroup).  Table chunks of 1024 float4 are owned round-robin: the owner
+ * sums the chunk's gradients over all ranks with peer loads, runs Adam on its shard of the optimizer state, stores the new
+ * parameters (+ fp16 copy) into every rank's buffers and zeroes every rank's gradient chunk; the MLP / variance block is
+ * reduced in rank order and updated identically on every rank; cross-GPU ordering by two flag barriers inside the kernel.
+ * Preconditions: h_ctx->flat_param / flat_grad / net.table_f16 are this rank's entries of the peer group and
+ * h_ctx->net_grad == h_ctx->flat_grad (the backward accumulates the folded-weight gradient into flat_grad[0:2432)).
+ * flags[r]: >= 17 zero-initialised u32 in rank r's symmetric buffer; counter: local zero-initialised u32.
+ * flags[rank][16] != 0 afterwards: a wait timed out (20 s) -- a peer never arrived. */
+#define SNB_MAX_PEERS 8
+typedef struct snb_peer_group {
+    int32_t world, rank;
+    float *param[SNB_MAX_PEERS];
+    float *grad[SNB_MAX_PEERS];
+    void *table_f16[SNB_MAX_PEERS];
+    uint32_t *flags[SNB_MAX_PEERS];
+    uint32_t *counter;
+} snb_peer_group;
+int32_t snb_train_tail_peer(const snb_train_ctx *h_ctx, const snb_peer_group *h_peers, float lr, int32_t step_count,
+                            const snb_dataset *h_ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,
+                            const snb_batch_out *h_out_next, snb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Mesh extraction.  Replaces extract_fields / extract_geometry (models/renderer.py:9-34): the 64^3-chunked SDF query
  * with a host round trip per chunk, and PyMCubes' CPU mcubes.marching_cubes (create_env.sh:14, models/renderer.py:29).

@@ -272,6 +272,214 @@ __global__ void __launch_bounds__(kTailThreads) train_tail_kernel(const __grid_c
     fold_store(L, s_p, s_norm, sqrtf(s_red[0] + s_red[1]), a.net, tid, kTailThreads);
 }
 
+// ---- data-parallel step tail over NVLink peer memory: gradient reduction + sharded Adam + parameter broadcast in ONE kernel ----
+// Every rank launches this kernel after its backward.  Flat parameters / gradients / fp16 table of all ranks live in a symmetric
+// (peer-mapped) allocation.  Chunk c (1024 float4) of the live table range is OWNED by rank c % world, statically, so Adam state is
+// sharded and never moves:
+//   owner: g = sum over ranks of grad_r[chunk] (peer loads, rank order), Adam on its own m / v / p, then stores the updated fp32
+//          parameters and the fp16 copy into EVERY rank's buffers and zeroes every rank's gradient chunk (it is its only reader);
+//   block 0 of every rank: sums all ranks' gradients w.r.t. the folded MLP weights (grad[0 : 2432), the inv_s gradient in slot
+//          kOffInvS) in rank order -- identical bits everywhere -- and runs the usual weight-norm backward / Adam / fold locally;
+//   sampler blocks as in train_tail_kernel.
+// Two cross-GPU barriers through flags in the symmetric buffer: "my backward is done" (written by block 0 at kernel start, awaited
+// by every reading block) and "all my remote stores are done" (written by block 0 after the local blocks have fenced and counted
+// in; block 0 leaves only when every rank has said so, which is what orders the next kernel behind the peers' parameter stores).
+// Replaces snb_unfold_grads -> NCCL allreduce (ring/tree over the whole range, every rank then repeating the full Adam sweep) ->
+// snb_train_tail.  Per GPU and step it moves (world-1)/world of the live range once in (gradients) and 2.5x that out
+// (parameters, fp16 copy, zeros) instead of the allreduce's 2x (world-1)/world in + out plus a full local Adam sweep.
+constexpr int kMaxPeers = SNB_MAX_PEERS;
+struct PeerArgs {
+    int world, rank;
+    float *param[kMaxPeers];
+    float *grad[kMaxPeers];
+    __half *f16[kMaxPeers];
+    uint32_t *flags[kMaxPeers];   // per rank: [0, 8) start flags, [8, 16) done flags, [16] error code
+    uint32_t *counter;            // local
+    uint32_t epoch;
+    int n_adam_blocks;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float *p) {   // system-scope load: never served from a stale L1 line
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_peer_f(const float *p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// threads 0 .. world-1 each wait for one rank's flag, then the CTA joins.  A wait longer than 20 s (a rank died) records an error
+// code instead of hanging the GPU; the host checks it when it reads the loss terms.
+__device__ __forceinline__ void wait_flags(const uint32_t *flags, uint32_t *err, int world, uint32_t epoch, uint32_t code) {
+    if ((int)threadIdx.x < world) {
+        const unsigned long long t0 = global_ns();
+        while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
+            if (global_ns() - t0 > 20000000000ull) { atomicExch(err, code + threadIdx.x); break; }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) train_tail_peer_kernel(const __grid_constant__ TailArgs a, const __grid_constant__ PeerArgs pg) {
+    const int tid = threadIdx.x;
+    uint32_t *my_flags = pg.flags[pg.rank];
+    if (blockIdx.x > (unsigned)a.n_sampler_blocks) {   // ---- owned table chunks: reduce, Adam, broadcast ----
+        wait_flags(my_flags, my_flags + 16, pg.world, pg.epoch, 100);
+        const int64_t b = blockIdx.x - 1 - a.n_sampler_blocks;
+        const int64_t base4 = a.small_pad >> 2, n4 = a.n_live >> 2, n_chunks = (n4 + kTailThreads - 1) / kTailThreads;
+        for (int64_t q = b;; q += pg.n_adam_blocks) {
+            const int64_t c = q * pg.world + pg.rank;
+            if (c >= n_chunks) break;
+            const int64_t j = c * kTailThreads + tid;   // float4 index inside the live table range
+            if (j >= n4) continue;
+            const int64_t i = base4 + j;
+            float4 gr[kMaxPeers];
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+                if (r < pg.world) gr[r] = ld_peer_f4(pg.grad[r] + 4 * i);
+            float4 P = reinterpret_cast<float4 *>(a.p)[i], M = reinterpret_cast<float4 *>(a.m)[i], V = reinterpret_cast<float4 *>(a.v)[i];
+            float4 G = gr[0];
+#pragma unroll
+            for (int r = 1; r < kMaxPeers; ++r)
+                if (r < pg.world) { G.x += gr[r].x; G.y += gr[r].y; G.z += gr[r].z; G.w += gr[r].w; }
+            adam_elem(a.coef, P.x, G.x, M.x, V.x);
+            adam_elem(a.coef, P.y, G.y, M.y, V.y);
+            adam_elem(a.coef, P.z, G.z, M.z, V.z);
+            adam_elem(a.coef, P.w, G.w, M.w, V.w);
+            reinterpret_cast<float4 *>(a.m)[i] = M;
+            reinterpret_cast<float4 *>(a.v)[i] = V;
+            const __half2 h0 = __floats2half2_rn(P.x, P.y), h1 = __floats2half2_rn(P.z, P.w);
+            uint2 hp;
+            hp.x = *reinterpret_cast<const uint32_t *>(&h0);
+            hp.y = *reinterpret_cast<const uint32_t *>(&h1);
+#pragma unroll
+            for (int r = 0; r < kMaxPeers; ++r)
+                if (r < pg.world) {
+                    reinterpret_cast<float4 *>(pg.param[r])[i] = P;
+                    reinterpret_cast<uint2 *>(pg.f16[r])[j] = hp;
+                    reinterpret_cast<float4 *>(pg.grad[r])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) atomicAdd(pg.counter, 1u);
+        return;
+    }
+    if (blockIdx.x >= 1) {   // ---- sampler for the next iteration ----
+        sample_patch_ray(a.ds, a.n_patches, a.seed, a.step, a.out, (blockIdx.x - 1) * kTailThreads + tid);
+        return;
+    }
+    // ---- block 0: barrier master + MLP / variance block ----
+    __shared__ float s_p[kSmallIters * kTailThreads], s_g[kSmallIters * kTailThreads], s_ng[kSmallIters * kTailThreads];
+    __shared__ float s_norm[kH], s_red[4];
+    const SmallLayout L(a.n_levels);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        a.g[kOffInvS] = a.stats[4];   // the inv_s gradient of this rank travels in the free slot of the folded-gradient block
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < pg.world) st_release_sys(pg.flags[tid] + pg.rank, pg.epoch);   // "my backward is complete"
+    float pr[kSmallIters], mr[kSmallIters], vr[kSmallIters], xr[kSmallIters];
+#pragma unroll
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        const bool in = e < L.n;
+        pr[k] = in ? a.p[e] : 0.f;
+        mr[k] = in ? a.m[e] : 0.f;
+        vr[k] = in ? a.v[e] : 0.f;
+    }
+    wait_flags(my_flags, my_flags + 16, pg.world, pg.epoch, 200);
+#pragma unroll
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        float part[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+            if (r < pg.world && e < kNetFloats) part[r] = ld_peer_f(pg.grad[r] + e);
+        float acc = 0.f;
+        if (e < kNetFloats) {
+            acc = part[0];
+#pragma unroll
+            for (int r = 1; r < kMaxPeers; ++r)
+                if (r < pg.world) acc += part[r];
+        }
+        xr[k] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        s_p[e] = pr[k];
+        s_ng[e] = xr[k];
+    }
+    __syncthreads();
+    const float d_inv_s = s_ng[kOffInvS];
+    for (int row = warp; row < kH; row += kTailThreads / 32) unfold_row(L, row, lane, s_p, s_ng, s_g);
+    {
+        float v1 = tid < kH ? s_p[L.v1 + tid] : 0.f, dw1 = tid < kH ? s_ng[kOffW1 + tid] : 0.f;
+        float ss1 = warp_sum_f(v1 * v1), dot1 = warp_sum_f(dw1 * v1);
+        if (warp < 2 && lane == 0) { s_red[warp] = ss1; s_red[2 + warp] = dot1; }
+    }
+    __syncthreads();
+    unfold_tail(L, tid, s_red[0] + s_red[1], s_red[2] + s_red[3], s_p, s_ng, d_inv_s, s_g);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSmallIters; ++k) {
+        const int e = tid + k * kTailThreads;
+        if (e < L.n) {
+            adam_elem(a.coef, pr[k], s_g[e], mr[k], vr[k]);
+            s_p[e] = pr[k];
+            a.p[e] = pr[k];
+            a.m[e] = mr[k];
+            a.v[e] = vr[k];
+        }
+    }
+    __syncthreads();
+    for (int row = warp; row < kH; row += kTailThreads / 32) {
+        float ss = row_sumsq(s_p + row * L.d_in, L.d_in, lane);
+        if (lane == 0) s_norm[row] = sqrtf(ss);
+    }
+    {
+        float v1n = tid < kH ? s_p[L.v1 + tid] : 0.f;
+        float ssn = warp_sum_f(v1n * v1n);
+        if (warp < 2 && lane == 0) s_red[warp] = ssn;
+    }
+    __syncthreads();
+    fold_store(L, s_p, s_norm, sqrtf(s_red[0] + s_red[1]), a.net, tid, kTailThreads);
+    // ---- all local chunk blocks have fenced their remote stores -> tell every rank; leave when every rank has told us ----
+    if (tid == 0) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_gpu(pg.counter) < (uint32_t)pg.n_adam_blocks) {
+            if (global_ns() - t0 > 20000000000ull) { atomicExch(my_flags + 16, 300u); break; }
+        }
+        *pg.counter = 0u;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < pg.world) st_release_sys(pg.flags[tid] + kMaxPeers + pg.rank, pg.epoch);
+    wait_flags(my_flags + kMaxPeers, my_flags + 16, pg.world, pg.epoch, 400);
+    for (int e = tid; e < kNetFloats; e += kTailThreads) a.g[e] = 0.f;   // every rank has read this block: ready for the next backward
+}
+
 }  // namespace snb
 using namespace snb;
 
@@ -359,5 +567,75 @@ extern "C" int32_t snb_train_tail(const snb_train_ctx *c, float lr, int32_t step
     if (adam_blocks > kNumSMs * 2) adam_blocks = kNumSMs * 2;
     train_tail_kernel<<<(unsigned)(1 + a.n_sampler_blocks + adam_blocks), kTailThreads, 0, S(stream)>>>(a);
     SNB_LAUNCH_CHECK("train_tail");
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_train_tail_peer(const snb_train_ctx *c, const snb_peer_group *pgrp, float lr, int32_t step_count,
+                                       const snb_dataset *ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,
+                                       const snb_batch_out *out_next, snb_stream_t stream) {
+    SNB_REQUIRE(c && pgrp, SNB_ERR_NULL, "train_tail_peer: null ctx / peer group");
+    SNB_REQUIRE(pgrp->world >= 1 && pgrp->world <= SNB_MAX_PEERS && pgrp->rank >= 0 && pgrp->rank < pgrp->world, SNB_ERR_ARG,
+                "train_tail_peer: bad world / rank");
+    SNB_REQUIRE(c->flat_param && c->flat_grad && c->exp_avg && c->exp_avg_sq && c->stats && c->net.net && c->net.table_f16 && pgrp->counter,
+                SNB_ERR_NULL, "train_tail_peer: null buffer");
+    for (int r = 0; r < pgrp->world; ++r)
+        SNB_REQUIRE(pgrp->param[r] && pgrp->grad[r] && pgrp->table_f16[r] && pgrp->flags[r], SNB_ERR_NULL, "train_tail_peer: null peer pointer");
+    SNB_REQUIRE(pgrp->param[pgrp->rank] == c->flat_param && pgrp->grad[pgrp->rank] == c->flat_grad && c->net_grad == c->flat_grad &&
+                    pgrp->table_f16[pgrp->rank] == c->net.table_f16, SNB_ERR_ARG,
+                "train_tail_peer: the context must use this rank's symmetric buffers, with net_grad aliased to flat_grad");
+    SNB_REQUIRE(step_count >= 1 && c->n_levels >= 1 && c->n_levels <= SNB_MAX_LEVELS && c->net.n_active <= (uint32_t)c->n_levels, SNB_ERR_ARG,
+                "train_tail_peer: bad step_count / level counts");
+    SNB_REQUIRE(c->small_pad % 4 == 0 && c->small_pad >= kSmallMax, SNB_ERR_ARG, "train_tail_peer: small_pad must be a multiple of 4 and >= 2435");
+    for (int r = 0; r < pgrp->world; ++r)
+        SNB_REQUIRE(aligned(pgrp->param[r], 16) && aligned(pgrp->grad[r], 16) && aligned(pgrp->table_f16[r], 8) && aligned(pgrp->flags[r], 4),
+                    SNB_ERR_ALIGN, "train_tail_peer: peer buffers must be 16-byte aligned");
+    SNB_REQUIRE(aligned(c->exp_avg, 16) && aligned(c->exp_avg_sq, 16), SNB_ERR_ALIGN, "train_tail_peer: buffers must be 16-byte aligned");
+    TailArgs a{};
+    const float beta1 = 0.9f, beta2 = 0.999f;
+    const double bc1 = 1.0 - pow((double)beta1, step_count), bc2 = 1.0 - pow((double)beta2, step_count);
+    a.coef = AdamCoef{beta1, beta2, 1e-8f, lr / (float)bc1, (float)(1.0 / sqrt(bc2)), 1.0f / (float)pgrp->world};
+    a.p = c->flat_param; a.g = c->flat_grad; a.m = c->exp_avg; a.v = c->exp_avg_sq;
+    a.p16 = (__half *)const_cast<void *>(c->net.table_f16);
+    a.small_pad = c->small_pad;
+    a.n_live = 2 * (int64_t)c->net.meta.offsets[c->net.n_active];
+    a.n_levels = c->n_levels;
+    a.do_unfold = 1;
+    a.net = const_cast<float *>(c->net.net);
+    a.net_grad = c->net_grad;
+    a.stats = c->stats;
+    if (ds_next && n_patches_next > 0) {
+        SNB_REQUIRE(out_next, SNB_ERR_NULL, "train_tail_peer: null sampler output");
+        SNB_REQUIRE(ds_next->W > 3 && ds_next->H > 3 && ds_next->n_train > 0 && ds_next->n_images > 0, SNB_ERR_ARG, "train_tail_peer: bad dataset sizes");
+        SNB_REQUIRE(ds_next->normals && ds_next->masks && ds_next->intrinsics_inv && ds_next->pose && ds_next->v_inverse && ds_next->train_ids,
+                    SNB_ERR_NULL, "train_tail_peer: null dataset tensor");
+        SNB_REQUIRE(out_next->rays_o && out_next->rays_d && out_next->plane_n && out_next->near_ && out_next->far_ && out_next->v_inv &&
+                        out_next->normal_gt && out_next->mask, SNB_ERR_NULL, "train_tail_peer: null sampler output tensor");
+        a.ds = *ds_next;
+        a.out = *out_next;
+        a.n_patches = n_patches_next;
+        a.seed = seed;
+        a.step = next_step;
+        a.n_sampler_blocks = (int)cdiv((int64_t)n_patches_next * SNB_PATCH, kTailThreads);
+    }
+    SNB_REQUIRE(a.n_sampler_blocks < kNumSMs - 8, SNB_ERR_ARG, "train_tail_peer: too many patches for the in-kernel sampler");
+    PeerArgs pa{};
+    pa.world = pgrp->world;
+    pa.rank = pgrp->rank;
+    for (int r = 0; r < pgrp->world; ++r) {
+        pa.param[r] = pgrp->param[r];
+        pa.grad[r] = pgrp->grad[r];
+        pa.f16[r] = (__half *)pgrp->table_f16[r];
+        pa.flags[r] = pgrp->flags[r];
+    }
+    pa.counter = pgrp->counter;
+    pa.epoch = (uint32_t)step_count;
+    // one CTA per SM at most (every waiting CTA is resident): block 0 + sampler blocks + chunk blocks <= 148
+    const int64_t n_chunks = cdiv(a.n_live / 4, (int64_t)kTailThreads);
+    int64_t own_chunks = cdiv(n_chunks, (int64_t)pgrp->world);
+    int64_t adam_blocks = own_chunks < 1 ? 1 : own_chunks;
+    if (adam_blocks > kNumSMs - 1 - a.n_sampler_blocks) adam_blocks = kNumSMs - 1 - a.n_sampler_blocks;
+    pa.n_adam_blocks = (int)adam_blocks;
+    train_tail_peer_kernel<<<(unsigned)(1 + a.n_sampler_blocks + adam_blocks), kTailThreads, 0, S(stream)>>>(a, pa);
+    SNB_LAUNCH_CHECK("train_tail_peer");
     return SNB_OK;
 }

@@ -39,6 +39,71 @@ def allreduce_live_gradients(flat_grad: torch.Tensor, n_live: int, world_size: i
 
 
 # ------------------------------------------------------------------------------------------------
+# peer-memory gradient exchange (NVLink / NVSwitch): symmetric allocation + static chunk ownership
+# ------------------------------------------------------------------------------------------------
+PEER_CHUNK_FLOATS = 4096     # 1024 float4: one CTA pass of train_tail_peer_kernel
+PEER_FLAG_WORDS = 32         # u32 per rank: [0,8) start flags, [8,16) done flags, [16] error code
+MAX_PEERS = 8
+
+
+def chunk_owner(chunk: int, world_size: int) -> int:
+    """Rank that reduces / updates / broadcasts table chunk `chunk` (static: Adam state of a parameter never moves, whatever the
+    number of active levels)."""
+    return chunk % world_size
+
+
+def owned_floats(n_live_table: int, rank: int, world_size: int) -> int:
+    """Floats of the live table range [0, n_live_table) whose Adam state lives on `rank`."""
+    n_chunks = -(-n_live_table // PEER_CHUNK_FLOATS)
+    total = 0
+    for c in range(rank, n_chunks, world_size):
+        total += min(PEER_CHUNK_FLOATS, n_live_table - c * PEER_CHUNK_FLOATS)
+    return total
+
+
+def carve_layout(sizes_bytes: Sequence[int], align: int = 256) -> Tuple[List[int], int]:
+    """Offsets of consecutive sub-buffers inside one allocation (each `align`-byte aligned) and the total size."""
+    offs, cur = [], 0
+    for nb in sizes_bytes:
+        cur = (cur + align - 1) // align * align
+        offs.append(cur)
+        cur += int(nb)
+    return offs, (cur + align - 1) // align * align
+
+
+class PeerGroup:
+    """One symmetric allocation per rank (torch.distributed._symmetric_memory: CUDA VMM memory mapped into every peer of the
+    box), carved into the buffers the peer tail kernel needs.  `ptrs(off)` = the device address of byte offset `off` in every
+    rank's allocation, as seen from THIS rank.  Raises if symmetric memory cannot be set up (the trainer then keeps NCCL)."""
+
+    def __init__(self, nbytes: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        self.buf = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        if self.world > MAX_PEERS:
+            raise RuntimeError(f"peer tail supports up to {MAX_PEERS} ranks")
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        own = self.buf.data_ptr()
+        off = own - ptrs[self.rank]          # the tensor may sit at an offset inside the exchanged allocation
+        if not (0 <= off and off + int(nbytes) <= int(self.hdl.buffer_size)):
+            raise RuntimeError("symmetric memory: tensor is not inside the exchanged allocation")
+        self.base = [p + off for p in ptrs]
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                  # nobody signals into a peer's flags before they are zeroed
+
+    def view(self, off: int, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        nb = numel * torch.empty((), dtype=dtype).element_size()
+        return self.buf[off:off + nb].view(dtype)
+
+    def ptrs(self, off: int) -> List[int]:
+        return [b + off for b in self.base]
+
+
+# ------------------------------------------------------------------------------------------------
 # mesh extraction: slab partition + gather/weld
 # ------------------------------------------------------------------------------------------------
 def slab_cells(resolution: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -62,6 +62,11 @@ class SnbTrainCtx(C.Structure):
                 ("res_z", C.c_int32)]
 
 
+class SnbPeerGroup(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("param", C.c_void_p * dp.MAX_PEERS), ("grad", C.c_void_p * dp.MAX_PEERS),
+                ("table_f16", C.c_void_p * dp.MAX_PEERS), ("flags", C.c_void_p * dp.MAX_PEERS), ("counter", C.c_void_p)]
+
+
 class SDFModel:
     """Parameters of SDFNetwork (models/fields.py:7-99, shipped configuration: one 64-wide hidden layer,
     weight-norm, Softplus(beta=100), input_concat, geometric init) + SingleVarianceNetwork
@@ -70,7 +75,10 @@ class SDFModel:
     so that Adam and the data-parallel allreduce are single contiguous sweeps.  A persistent fp16 copy
     of the table (what tiny-cuda-nn gathers from) is refreshed by the optimizer kernel."""
 
-    def __init__(self, encoding_config: dict, bias: float = 0.6, variance_init: float = 0.5, seed: int = 1337, device="cuda"):
+    def __init__(self, encoding_config: dict, bias: float = 0.6, variance_init: float = 0.5, seed: int = 1337, device="cuda",
+                 peer_group_factory=None):
+        """peer_group_factory(nbytes) -> dp.PeerGroup: put parameters, gradients and the fp16 table into a symmetric (peer-mapped)
+        allocation so that the data-parallel tail kernel (snb_train_tail_peer) can reduce / broadcast them over NVLink."""
         cfg = dict(encoding_config)
         self.n_levels = int(cfg["n_levels"])
         assert int(cfg.get("n_features_per_level", 2)) == 2
@@ -96,13 +104,27 @@ class SDFModel:
         flat[o["g1"]] = w1.norm()
         flat[o["b1"]] = -bias
         flat[o["var"]] = variance_init
-        self.flat = flat.to(self.device)
-        self.grad = torch.zeros_like(self.flat)
+        self.peer = None
+        if peer_group_factory is not None:
+            n_flat = SMALL_PAD + self.n_table
+            offs, total = dp.carve_layout([n_flat * 4, n_flat * 4, self.n_table * 2, dp.PEER_FLAG_WORDS * 4, 256])
+            pg = peer_group_factory(total)            # zero-filled, all ranks synchronised
+            self.peer, self.peer_offsets = pg, offs
+            self.flat = pg.view(offs[0], n_flat, torch.float32)
+            self.flat.copy_(flat)
+            self.grad = pg.view(offs[1], n_flat, torch.float32)
+            self.table_f16 = pg.view(offs[2], self.n_table, torch.float16)
+            self.peer_flags = pg.view(offs[3], dp.PEER_FLAG_WORDS, torch.int32)
+            self.peer_counter = pg.view(offs[4], 1, torch.int32)
+            self.net_grad = self.grad[:NET_FLOATS]    # the backward accumulates the folded-weight gradient where the peers read it
+        else:
+            self.flat = flat.to(self.device)
+            self.grad = torch.zeros_like(self.flat)
+            self.table_f16 = torch.empty(self.n_table, dtype=torch.float16, device=self.device)
+            self.net_grad = torch.zeros(NET_FLOATS, device=self.device)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        self.table_f16 = torch.empty(self.n_table, dtype=torch.float16, device=self.device)
         self.net = torch.zeros(NET_FLOATS, device=self.device)
-        self.net_grad = torch.zeros(NET_FLOATS, device=self.device)
         self.n_active = 0  # SDFNetwork.bindwidth
         self.net_stale = True  # `net` / `net_grad` are not (folded current parameters / zero): the lean step calls prep() first
         self.refresh_table_f16()
@@ -125,6 +147,11 @@ class SDFModel:
 
     def refresh_table_f16(self):
         call("snb_cast_f32_to_f16", self.n_table, ptr(self.table), ptr(self.table_f16))
+
+    def peer_struct(self) -> SnbPeerGroup:
+        pg, o = self.peer, self.peer_offsets
+        arr = lambda off: (C.c_void_p * dp.MAX_PEERS)(*(pg.ptrs(off) + [None] * (dp.MAX_PEERS - pg.world)))
+        return SnbPeerGroup(pg.world, pg.rank, arr(o[0]), arr(o[1]), arr(o[2]), arr(o[3]), self.peer_counter.data_ptr())
 
     def net_struct(self) -> SnbNet:
         return SnbNet(self.table_f16.data_ptr(), self.net.data_ptr(), self.meta, self.n_active)
@@ -334,7 +361,28 @@ class FusedTrainer:
         self.n_patches = int(conf["batch_size"])
         assert int(conf["patch_size"]) == 3, "3x3 patches (config/diligent.conf:29)"
         assert conf.get("gradient_method", "dfd") == "dfd", "fused path implements dfd (the shipped default)"
-        self.model = SDFModel(conf["encoding"], conf["sdf_network"]["bias"], conf["variance_init"], device=self.device)
+        # data parallel: gradient reduction + sharded Adam + parameter broadcast inside ONE kernel over NVLink peer memory
+        # (SNB_DP=peer, default) or NCCL allreduce + replicated Adam (SNB_DP=nccl, also the fallback when symmetric memory is unavailable)
+        self.peer_mode = False
+        self.model = None
+        if world_size > 1 and os.environ.get("SNB_DP", "peer") == "peer":
+            import torch.distributed as dist
+            ok = 1
+            try:
+                self.model = SDFModel(conf["encoding"], conf["sdf_network"]["bias"], conf["variance_init"], device=self.device,
+                                      peer_group_factory=lambda nbytes: dp.PeerGroup(nbytes, self.device))
+            except Exception as e:   # noqa: BLE001 -- any failure of the symmetric-memory setup selects the NCCL path, loudly
+                import sys
+                print(f"[supernormal_b200] rank {rank}: peer-memory data parallelism unavailable ({type(e).__name__}: {e}); using NCCL allreduce",
+                      file=sys.stderr)
+                ok, self.model = 0, None
+            flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # every rank takes the same path
+            self.peer_mode = bool(flag.item())
+            if not self.peer_mode:
+                self.model = None
+        if self.model is None:
+            self.model = SDFModel(conf["encoding"], conf["sdf_network"]["bias"], conf["variance_init"], device=self.device)
         rm = conf["ray_marching"]
         self.start_step, self.end_step = float(rm["start_step_size"]), float(rm["end_step_size"])
         self.slop = (math.log10(self.start_step) - math.log10(self.end_step)) / conf["end_iter"]
@@ -344,7 +392,7 @@ class FusedTrainer:
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
         self.seed = dp.rank_seed(seed, rank)   # every rank draws its own patches (weak scaling)
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
-        self.lean = os.environ.get("SNB_LEAN", "1") != "0"   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
+        self.lean = self.peer_mode or os.environ.get("SNB_LEAN", "1") != "0"   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
                                       # (snb_train_tail) unfolds, runs Adam, folds the updated weights and pre-samples the next batch
         self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
         self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
@@ -372,6 +420,11 @@ class FusedTrainer:
         self.gen = torch.Generator(device=self.device).manual_seed(seed + rank)
         self.np_rng = np.random.RandomState(seed + rank)
         self.last_batch = None
+        if self.peer_mode:
+            import torch.distributed as dist
+            self._peer_struct = self.model.peer_struct()
+            torch.cuda.synchronize(self.device)
+            dist.barrier()           # every rank's parameters are in place before anyone's first peer kernel
 
     @property
     def own_batch(self) -> Dict[str, torch.Tensor]:
@@ -443,6 +496,7 @@ class FusedTrainer:
         weights -- optimizer_step's tail kernel unfolds it."""
         m, b = self.model, self.buf
         c = self.conf
+        assert lean or not self.peer_mode, "peer-memory data parallelism runs the lean step only (net_grad aliases the gradient buffer)"
         self.last_batch = batch
         self._grads_folded = lean
         if lean and m.net_stale:
@@ -495,6 +549,16 @@ class FusedTrainer:
             call("snb_train_optim", C.byref(ctx), float(self.lr), t, gscale)   # one Adam sweep: MLP block + live table levels + fp16 refresh
             m.net_stale = True
             return
+        nxt = 1 - self._slot
+        if self.peer_mode:   # reduction over NVLink peer memory, sharded Adam, parameter broadcast, fold, next batch: one launch
+            if presample_next:
+                call("snb_train_tail_peer", C.byref(ctx), C.byref(self._peer_struct), float(self.lr), t, C.byref(self.ds_struct), self.n_patches,
+                     self.seed, self.iter_step + 1, C.byref(self._out_structs[nxt]))
+                self._presampled = (self.iter_step + 1, nxt)
+            else:
+                call("snb_train_tail_peer", C.byref(ctx), C.byref(self._peer_struct), float(self.lr), t, None, 0, 0, 0, None)
+            self._grads_folded = False
+            return
         unfolded = 0
         gscale = 1.0
         if self.world_size > 1:   # the allreduce works on (v, g, b, variance) gradients: unfold first, tail skips its unfold
@@ -502,7 +566,6 @@ class FusedTrainer:
             gscale = dp.allreduce_live_gradients(m.grad, n_live, self.world_size)
             unfolded = 1
         if presample_next:
-            nxt = 1 - self._slot
             call("snb_train_tail", C.byref(ctx), float(self.lr), t, gscale, unfolded, C.byref(self.ds_struct), self.n_patches, self.seed,
                  self.iter_step + 1, C.byref(self._out_structs[nxt]))
             self._presampled = (self.iter_step + 1, nxt)
@@ -534,7 +597,15 @@ class FusedTrainer:
         return HostBatchFeeder(self, depth, log_capacity)
 
     # -- host-side readbacks (sync) ---------------------------------------------------------------
+    def check_peer_error(self) -> None:
+        """Raises if a cross-GPU wait inside the peer tail kernel timed out (a rank never arrived)."""
+        if self.peer_mode:
+            code = int(self.model.peer_flags[16].item())
+            if code:
+                raise RuntimeError(f"snb_train_tail_peer: wait timed out (code {code}: 1xx/2xx start barrier, 300 local blocks, 4xx done barrier)")
+
     def loss_terms(self) -> Dict[str, float]:
+        self.check_peer_error()
         st = self.buf.stats.cpu().tolist()
         tot = self.buf.totals.cpu().tolist()
         S = max(tot[0], 1)
