@@ -48,8 +48,36 @@ class ClockSampler:
     def __init__(self, gpu_index=0):
         self.gpu, self.rows, self.proc = gpu_index, [], None
         self.t0 = self.t1 = None
+        self.nv_rows, self._stop, self.nv_thread = [], threading.Event(), None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids and all(v.isdigit() for v in ids) and self.gpu < len(ids):
+            return int(ids[self.gpu])
+        return self.gpu
+
+    def _nvml_loop(self):
+        """In-process NVML polling (every 10 ms): the same fields as the nvidia-smi poller without its process start-up and
+        per-row latency, which at 8 ranks can exceed a 300 ms timed region.  Any NVML failure leaves the nvidia-smi rows."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+            while not self._stop.is_set():
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                self.nv_rows.append((time.time(), sm, mx, [k for k, b in bits.items() if r & b]))
+                time.sleep(0.01)
+        except Exception:
+            pass
 
     def start(self):
+        self.nv_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+        self.nv_thread.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -70,12 +98,19 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
+        self._stop.set()
+        if self.nv_thread is not None:
+            self.nv_thread.join(timeout=1)
         if self.proc:
             time.sleep(0.12)          # let the row that covers the end of the region arrive
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
+        nv = [r for r in self.nv_rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        if nv:
+            return {"sm_mhz": float(np.median([r[1] for r in nv])), "sm_max_mhz": max(r[2] for r in nv),
+                    "reasons": sorted({x for r in nv for x in r[3]}), "samples": len(nv), "window": "timed region", "source": "nvml"}
         ok = [r for ts, r in self.rows if len(r) >= 9 and self.t0 is not None and self.t0 <= ts <= (self.t1 or ts) + 0.06]
         where = "timed region"
         if not ok:   # region shorter than the polling period: take the rows closest to it
@@ -228,7 +263,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    clk = ClockSampler(local).start()
+    clk = ClockSampler(local)
+    if rank == 0:   # rank 0 prints the line; one poller per box
+        clk.start()
     for _ in range(W):
         tr.train_step()
     # ---- timed region: device-resident sampling ----------------------------------------------

@@ -646,15 +646,14 @@ class FusedTrainer:
     def profile_kernels(self, steps: int = 20) -> dict:
         """Per-entry-point device time (CUDA events on the launching stream) over `steps` real iterations."""
         _lib.PROFILE = []
-        S_acc = E_acc = 0
-        saved, self.fused_host = self.fused_host, False   # per-kernel entry points so each launch can be bracketed
-        try:
+        acc = torch.zeros(2, dtype=torch.int64, device=self.device)   # sample / end counts summed on the device: no host sync per
+        saved, self.fused_host = self.fused_host, False               # step (data-parallel ranks would drift apart); per-kernel entry
+        try:                                                           # points so each launch can be bracketed
             for _ in range(steps):
                 self.train_step()
-                tot = self.buf.totals.tolist()
-                S_acc += tot[0]
-                E_acc += tot[1]
+                acc += self.buf.totals[:2]
             torch.cuda.synchronize()
+            S_acc, E_acc = (int(v) for v in acc.tolist())
             rec = _lib.PROFILE
         finally:
             _lib.PROFILE = None
@@ -667,6 +666,8 @@ class FusedTrainer:
         out = {"us_per_step": {k: round(v, 2) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
                "sum_us_per_step": round(total, 2), "avg_samples": S_acc / steps, "avg_ends": E_acc / steps,
                "n_active": self.model.n_active}
+        if self.peer_mode:
+            out["note"] = "snb_train_tail_peer includes the in-kernel wait for the slowest rank (the two cross-GPU barriers)"
         S, E = int(S_acc / steps), int(E_acc / steps)
         out["hbm_model"] = {}
         for name in sorted(per_step, key=lambda k: -per_step[k]):
