@@ -85,3 +85,71 @@ def _mesh_case(rank, world):
 def test_slab_mesh_gather(world):
     out = _run(_mesh_case, world)
     assert all(out[r] is True for r in range(world))
+
+
+# ---- peer-memory step tail (snb_train_tail_peer): static chunk ownership, sharded Adam, broadcast -- host-side restatement ----
+def test_peer_chunk_ownership_partitions_live_range():
+    from supernormal_b200 import dp
+    for world in (1, 2, 3, 8):
+        for n_live in (0, 4, 4096, 4100, 3 * 4096 + 8, 1_000_000, 23_744_000):
+            assert sum(dp.owned_floats(n_live, r, world) for r in range(world)) == n_live
+        # static: the owner of a chunk does not depend on how many levels are live
+        assert [dp.chunk_owner(c, world) for c in range(2 * world)] == list(range(world)) * 2
+    offs, total = dp.carve_layout([10, 4096, 1, 128])
+    assert offs == [0, 256, 4352, 4608] and total == 4864 and all(o % 256 == 0 for o in offs)
+
+
+def _adam(p, g, m, v, lr, t, scale):
+    g = g * scale
+    m = 0.9 * m + 0.1 * g
+    v = 0.999 * v + 0.001 * g * g
+    bc1, bc2 = 1 - 0.9 ** t, 1 - 0.999 ** t
+    return p - lr / bc1 * m / (v.sqrt() / bc2 ** 0.5 + 1e-8), m, v
+
+
+def _peer_tail_case(rank, world):
+    """What the peer kernel does, with torch collectives standing in for peer loads / stores: the owner of each 4096-float
+    chunk sums that chunk's gradients over the ranks in rank order, runs Adam on ITS shard of the state and broadcasts the
+    new parameters; compared with all-reduce + replicated Adam."""
+    from supernormal_b200 import dp
+    n_live, n = 3 * dp.PEER_CHUNK_FLOATS + 1000, 5 * dp.PEER_CHUNK_FLOATS
+    gen = torch.Generator().manual_seed(7)
+    p0 = torch.randn(n, generator=gen, dtype=torch.float64)
+    m0, v0 = torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    p_ref, m_ref, v_ref = p0.clone(), m0.clone(), v0.clone()
+    p, m, v = p0.clone(), m0.clone(), v0.clone()          # m, v: only the owned chunks are ever touched on this rank
+    chunk = torch.arange(n) // dp.PEER_CHUNK_FLOATS
+    mine = (chunk % world == rank) & (torch.arange(n) < n_live)
+    for t in (1, 2, 3):
+        g = torch.randn(n, generator=torch.Generator().manual_seed(100 * t + rank), dtype=torch.float64)
+        g[n_live:] = 0.0
+        # reference path: all-reduce, every rank repeats the whole Adam sweep
+        gs = g.clone()
+        dist.all_reduce(gs)
+        pr, mr, vr = _adam(p_ref[:n_live], gs[:n_live], m_ref[:n_live], v_ref[:n_live], 1e-2, t, 1.0 / world)
+        p_ref[:n_live], m_ref[:n_live], v_ref[:n_live] = pr, mr, vr
+        # peer path: "peer loads" of every rank's gradient, rank-order sum on the owner, Adam on the shard, broadcast
+        all_g = [torch.zeros_like(g) for _ in range(world)]
+        dist.all_gather(all_g, g)
+        gsum = all_g[0].clone()
+        for r in range(1, world):
+            gsum += all_g[r]
+        pn, mn, vn = _adam(p[mine], gsum[mine], m[mine], v[mine], 1e-2, t, 1.0 / world)
+        m[mine], v[mine] = mn, vn
+        contrib = torch.zeros_like(p)
+        contrib[mine] = pn
+        dist.all_reduce(contrib)                           # every element of the live range has exactly one owner
+        p[:n_live] = contrib[:n_live]
+    return p.tolist(), p_ref.tolist(), int(mine.sum())
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_tail_ownership_equals_allreduce_adam(world):
+    from supernormal_b200 import dp
+    out = _run(_peer_tail_case, world)
+    n_live = 3 * dp.PEER_CHUNK_FLOATS + 1000
+    assert sum(out[r][2] for r in range(world)) == n_live
+    for r in range(world):
+        assert out[r][0] == out[0][0]                      # replicas bit-identical
+        np.testing.assert_allclose(out[r][0], out[r][1], rtol=1e-12, atol=1e-12)   # == all-reduce + replicated Adam
+    assert out[0][0][n_live:] == out[0][1][n_live:]       # inactive levels untouched
