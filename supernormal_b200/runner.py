@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import mesh
+from . import mesh, mesh_post
 from ._lib import call, ptr
 from .trainer import FusedTrainer, P, make_batch_struct
 
@@ -80,6 +80,25 @@ def eval_mae(tr: FusedTrainer) -> Dict[str, float]:
     if errs_test:
         out["mae_testview"] = float(torch.cat(errs_test).mean())
     return out
+
+
+@torch.no_grad()
+def validate_mesh(tr: FusedTrainer, resolution: int = 512, threshold: float = 0.0):
+    """Runner.validate_mesh (exp_runner.py:483-506) without the file I/O: extract_geometry on the object bounding box, then
+    remove_isolated_clusters (largest edge-connected cluster).  -> (vertices float64 [V,3], triangles int32 [T,3]); None on
+    ranks > 0 of a data-parallel run."""
+    res = mesh.extract_geometry(tr.model, tr.ds.object_bbox_min, tr.ds.object_bbox_max, resolution, threshold)
+    if res is None:
+        return None
+    return mesh_post.remove_isolated_clusters(*res)
+
+
+@torch.no_grad()
+def find_visible_points(tr: FusedTrainer, resolution_level: int = 1) -> np.ndarray:
+    """Runner.find_visible_points (exp_runner.py:580-592): the surface point behind every foreground pixel of every view, by sphere
+    tracing the SDF (mesh_post.find_visible_points) -- the points Chamfer distance / F-score are computed on (:573-577)."""
+    tr.model.prep()
+    return mesh_post.find_visible_points(tr.ds, lambda x: tr.model.sdf(x), resolution_level=resolution_level).cpu().numpy()
 
 
 def chamfer_distance_and_f1_score(ref_points: np.ndarray, eval_points: np.ndarray, f_threshold: float = 0.5):
