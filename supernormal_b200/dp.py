@@ -61,6 +61,11 @@ def owned_floats(n_live_table: int, rank: int, world_size: int) -> int:
     return total
 
 
+def owner_mask(n: int, rank: int, world_size: int, device=None) -> torch.Tensor:
+    """bool[n]: table floats whose chunk is owned by `rank` (chunk c = floats [4096 c, 4096 (c+1)))."""
+    return (torch.arange(n, device=device) // PEER_CHUNK_FLOATS) % world_size == rank
+
+
 def carve_layout(sizes_bytes: Sequence[int], align: int = 256) -> Tuple[List[int], int]:
     """Offsets of consecutive sub-buffers inside one allocation (each `align`-byte aligned) and the total size."""
     offs, cur = [], 0

@@ -592,6 +592,56 @@ class FusedTrainer:
         self.iter_step += 1
         self.lr = self.conf["learning_rate"] * self._lr_factor()
 
+    # -- checkpoint / resume -------------------------------------------------------
+    def state_dict(self) -> dict:
+        """What Runner.save_checkpoint stores (exp_runner.py:298-315: both networks, the optimizer, iter_step) under the
+        reference's keys, plus what it forgets and a resume needs: the occupancy grid (the reference restarts from an all-empty
+        grid after is_continue) and the number of active levels.  Collective in a data-parallel run with the peer-memory tail:
+        the table's Adam state is sharded by chunk owner and is summed back together (non-owned chunks are exactly zero)."""
+        m = self.model
+        ea, eas = m.exp_avg.clone(), m.exp_avg_sq.clone()
+        if self.peer_mode:
+            import torch.distributed as dist
+            for t in (ea, eas):
+                small = t[:SMALL_PAD].clone()    # the MLP block is updated identically on every rank: not summed
+                t[:SMALL_PAD] = 0
+                dist.all_reduce(t)
+                t[:SMALL_PAD] = small
+        sd = m.reference_state_dict()
+        sd["optimizer"] = {"exp_avg": ea, "exp_avg_sq": eas, "step": self.iter_step}
+        sd["iter_step"] = self.iter_step
+        sd["n_active"] = m.n_active
+        sd["occupancy_grid"] = {"occs": self.grid.occs.clone(), "binary": self.grid._binary.clone()}
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        """Resume: parameters, Adam moments, schedule position (step size, learning rate, active levels are functions of
+        iter_step) and the occupancy grid.  The patch stream is counter-based (seed, iteration), so a resumed run draws the
+        batches the uninterrupted run would have drawn."""
+        m = self.model
+        m.load_reference_state_dict(sd)
+        opt = sd["optimizer"]
+        m.exp_avg.copy_(opt["exp_avg"].to(self.device))
+        m.exp_avg_sq.copy_(opt["exp_avg_sq"].to(self.device))
+        if self.peer_mode:   # keep only the chunks this rank owns
+            mine = dp.owner_mask(m.n_table, self.rank, self.world_size, self.device)
+            m.exp_avg[SMALL_PAD:] *= mine
+            m.exp_avg_sq[SMALL_PAD:] *= mine
+        m.grad.zero_()
+        self.iter_step = int(sd["iter_step"])
+        m.n_active = int(sd["n_active"])
+        self.lr = float(self.conf["learning_rate"]) * (self._lr_factor() if self.iter_step > 0 else 1.0)
+        self.grid.occs.copy_(sd["occupancy_grid"]["occs"].to(self.device))
+        self.grid._binary.copy_(sd["occupancy_grid"]["binary"].to(self.device))
+        self.occ_ws.zero_()     # workspace of the fused occupancy update: [sum of occs (f64) | number of occupied cells (u64)]
+        self.occ_ws.view(torch.int64)[1] = int(self.grid._binary.sum().item())
+        self._presampled = (-1, 0)
+        if self.peer_mode:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier()
+
     # -- host-fed training (the end-to-end path: batches arrive in HOST memory, losses go back to the host) -----------
     def host_feeder(self, depth: int = 2, log_capacity: int = 4096) -> "HostBatchFeeder":
         return HostBatchFeeder(self, depth, log_capacity)

@@ -95,6 +95,10 @@ def test_peer_chunk_ownership_partitions_live_range():
             assert sum(dp.owned_floats(n_live, r, world) for r in range(world)) == n_live
         # static: the owner of a chunk does not depend on how many levels are live
         assert [dp.chunk_owner(c, world) for c in range(2 * world)] == list(range(world)) * 2
+    for world in (2, 3):   # owner_mask is the elementwise form of owned_floats
+        masks = [dp.owner_mask(3 * 4096 + 8, r, world) for r in range(world)]
+        assert torch.stack(masks).sum(0).eq(1).all()
+        assert [int(mk.sum()) for mk in masks] == [dp.owned_floats(3 * 4096 + 8, r, world) for r in range(world)]
     offs, total = dp.carve_layout([10, 4096, 1, 128])
     assert offs == [0, 256, 4352, 4608] and total == 4864 and all(o % 256 == 0 for o in offs)
 

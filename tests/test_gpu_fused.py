@@ -564,3 +564,31 @@ def test_single_launch_compaction_equals_scan_then_compact(cuda, cap):
     for k in outs:
         assert torch.equal(got[k], ref[k]), k
     assert b.stats[0].item() == pytest.approx((batch["mask"] > 0.5).sum().item() + 1e-5) and (b.stats[1:] == 0).all()
+
+
+def test_checkpoint_resume_continues_training(cuda):
+    """FusedTrainer.state_dict / load_state_dict (exp_runner.py:298-315 + the occupancy grid): a fresh trainer resumed from the
+    checkpoint holds the same bits and its next iteration sees the same batch, the same samples and the same loss."""
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    conf = dict(DILIGENT_CONF, batch_size=256, end_iter=200, increase_bindwidth_every=5, warm_up_end=10)
+    a = FusedTrainer(ds, conf, device=cuda)
+    for _ in range(20):
+        a.train_step()
+    sd = a.state_dict()
+    assert {"sdf_network_fine", "variance_network_fine", "optimizer", "iter_step", "occupancy_grid"} <= set(sd)
+    b = FusedTrainer(ds, conf, device=cuda)
+    b.load_state_dict({k: ({kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if isinstance(v, dict) else v)
+                       for k, v in sd.items()})   # through host memory, like torch.save / torch.load
+    assert b.iter_step == 20 and b.model.n_active == a.model.n_active == 4 and b.lr == pytest.approx(a.lr, rel=1e-12)
+    for name in ("flat", "exp_avg", "exp_avg_sq", "table_f16"):
+        assert torch.equal(getattr(a.model, name), getattr(b.model, name)), name
+    assert torch.equal(a.grid.binary, b.grid.binary) and torch.equal(a.grid.occs, b.grid.occs)
+    a.train_step()
+    b.train_step()
+    for k in a.own_batch:
+        assert torch.equal(torch.nan_to_num(a.own_batch[k]), torch.nan_to_num(b.own_batch[k])), k
+    assert a.buf.totals.tolist() == b.buf.totals.tolist()          # same parameters, grid and batch: same samples
+    la, lb = a.loss_terms(), b.loss_terms()
+    assert lb["loss"] == pytest.approx(la["loss"], rel=1e-4) and a.iter_step == b.iter_step == 21
