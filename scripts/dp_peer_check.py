@@ -34,14 +34,15 @@ def make(mode):
 def replicas_identical(tr):
     """every rank holds the same bits"""
     m = tr.model
-    sig = torch.stack([m.flat.view(torch.int32).long().sum(), m.table_f16.view(torch.int16).long().sum(), m.net.view(torch.int32).long().sum(),
-                       m.flat.view(torch.int32).long().mul(torch.arange(m.flat.numel(), device=dev) % 8191).sum()])
+    flat = torch.cat([m.flat[:m.n_small], m.gather_table()])   # gather_table: collective only with SNB_PEER_F16ONLY=1
+    sig = torch.stack([flat.view(torch.int32).long().sum(), m.table_f16.view(torch.int16).long().sum(), m.net.view(torch.int32).long().sum(),
+                       flat.view(torch.int32).long().mul(torch.arange(flat.numel(), device=dev) % 8191).sum()])
     all_sig = [torch.zeros_like(sig) for _ in range(world)]
     dist.all_gather(all_sig, sig)
     return all(torch.equal(all_sig[0], s) for s in all_sig)
 
 
-out = {"world": world}
+out = {"world": world, "peer_f16_only": os.environ.get("SNB_PEER_F16ONLY", "0")}
 A, B = make("peer"), make("nccl")
 out["peer_mode"] = [A.peer_mode, B.peer_mode]
 ident, close, losses = [], [], []
@@ -50,7 +51,7 @@ for it in range(a.check_steps):
     B.train_step()
     if it in (0, 1, a.check_steps - 1):
         ident.append((replicas_identical(A), replicas_identical(B)))
-        close.append(((A.model.flat - B.model.flat).abs() > 1e-6).float().mean().item())
+        close.append(((A.model.gather_table() - B.model.gather_table()).abs() > 1e-6).float().mean().item())
     la, lb = A.loss_terms(), B.loss_terms()
     losses.append((la["loss"], lb["loss"], la["n_samples"], lb["n_samples"]))
 out["replicas_identical_peer_nccl"] = ident

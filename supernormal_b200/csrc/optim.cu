@@ -339,6 +339,10 @@ __device__ __forceinline__ void wait_flags(const uint32_t *flags, uint32_t *err,
     __syncthreads();
 }
 
+// kF16Only (experimental, snb_peer_group.table_f16_only; NOT yet validated on a GPU -- see DESIGN.md section 6): the owner keeps the fp32
+// master parameters of its chunks to itself and broadcasts only the fp16 copy the forward gathers from, and every rank zeroes its own
+// gradient range after the done barrier instead of the owner zeroing it remotely: 2 instead of 14 bytes per owned parameter leave the GPU.
+template <bool kF16Only>
 __global__ void __launch_bounds__(kTailThreads, 1) train_tail_peer_kernel(const __grid_constant__ TailArgs a, const __grid_constant__ PeerArgs pg) {
     const int tid = threadIdx.x;
     uint32_t *my_flags = pg.flags[pg.rank];
@@ -371,17 +375,23 @@ __global__ void __launch_bounds__(kTailThreads, 1) train_tail_peer_kernel(const 
             uint2 hp;
             hp.x = *reinterpret_cast<const uint32_t *>(&h0);
             hp.y = *reinterpret_cast<const uint32_t *>(&h1);
+            if (kF16Only) reinterpret_cast<float4 *>(a.p)[i] = P;
 #pragma unroll
             for (int r = 0; r < kMaxPeers; ++r)
                 if (r < pg.world) {
-                    reinterpret_cast<float4 *>(pg.param[r])[i] = P;
+                    if (!kF16Only) reinterpret_cast<float4 *>(pg.param[r])[i] = P;
                     reinterpret_cast<uint2 *>(pg.f16[r])[j] = hp;
-                    reinterpret_cast<float4 *>(pg.grad[r])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!kF16Only) reinterpret_cast<float4 *>(pg.grad[r])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         }
         __threadfence_system();
         __syncthreads();
         if (tid == 0) atomicAdd(pg.counter, 1u);
+        if (kF16Only) {   // every rank has finished reading this rank's gradients once all done flags are up: zero them locally
+            wait_flags(my_flags + kMaxPeers, my_flags + 16, pg.world, pg.epoch, 500);
+            for (int64_t j = b * kTailThreads + tid; j < n4; j += (int64_t)pg.n_adam_blocks * kTailThreads)
+                reinterpret_cast<float4 *>(a.g)[base4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         return;
     }
     if (blockIdx.x >= 1) {   // ---- sampler for the next iteration ----
@@ -635,7 +645,10 @@ extern "C" int32_t snb_train_tail_peer(const snb_train_ctx *c, const snb_peer_gr
     int64_t adam_blocks = own_chunks < 1 ? 1 : own_chunks;
     if (adam_blocks > kNumSMs - 1 - a.n_sampler_blocks) adam_blocks = kNumSMs - 1 - a.n_sampler_blocks;
     pa.n_adam_blocks = (int)adam_blocks;
-    train_tail_peer_kernel<<<(unsigned)(1 + a.n_sampler_blocks + adam_blocks), kTailThreads, 0, S(stream)>>>(a, pa);
+    if (pgrp->table_f16_only)
+        train_tail_peer_kernel<true><<<(unsigned)(1 + a.n_sampler_blocks + adam_blocks), kTailThreads, 0, S(stream)>>>(a, pa);
+    else
+        train_tail_peer_kernel<false><<<(unsigned)(1 + a.n_sampler_blocks + adam_blocks), kTailThreads, 0, S(stream)>>>(a, pa);
     SNB_LAUNCH_CHECK("train_tail_peer");
     return SNB_OK;
 }

@@ -64,7 +64,8 @@ class SnbTrainCtx(C.Structure):
 
 class SnbPeerGroup(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("param", C.c_void_p * dp.MAX_PEERS), ("grad", C.c_void_p * dp.MAX_PEERS),
-                ("table_f16", C.c_void_p * dp.MAX_PEERS), ("flags", C.c_void_p * dp.MAX_PEERS), ("counter", C.c_void_p)]
+                ("table_f16", C.c_void_p * dp.MAX_PEERS), ("flags", C.c_void_p * dp.MAX_PEERS), ("counter", C.c_void_p),
+                ("table_f16_only", C.c_int32)]
 
 
 class SDFModel:
@@ -117,6 +118,9 @@ class SDFModel:
             self.peer_flags = pg.view(offs[3], dp.PEER_FLAG_WORDS, torch.int32)
             self.peer_counter = pg.view(offs[4], 1, torch.int32)
             self.net_grad = self.grad[:NET_FLOATS]    # the backward accumulates the folded-weight gradient where the peers read it
+            # experimental (not yet validated on a GPU): owners broadcast only the fp16 table copy; fp32 table parameters are then valid
+            # on the owner's chunks only and gather_table() reassembles them
+            self.peer_f16_only = os.environ.get("SNB_PEER_F16ONLY", "0") == "1"
         else:
             self.flat = flat.to(self.device)
             self.grad = torch.zeros_like(self.flat)
@@ -151,7 +155,19 @@ class SDFModel:
     def peer_struct(self) -> SnbPeerGroup:
         pg, o = self.peer, self.peer_offsets
         arr = lambda off: (C.c_void_p * dp.MAX_PEERS)(*(pg.ptrs(off) + [None] * (dp.MAX_PEERS - pg.world)))
-        return SnbPeerGroup(pg.world, pg.rank, arr(o[0]), arr(o[1]), arr(o[2]), arr(o[3]), self.peer_counter.data_ptr())
+        return SnbPeerGroup(pg.world, pg.rank, arr(o[0]), arr(o[1]), arr(o[2]), arr(o[3]), self.peer_counter.data_ptr(),
+                            int(self.peer_f16_only))
+
+    @torch.no_grad()
+    def gather_table(self) -> torch.Tensor:
+        """The full fp32 table on every rank.  Collective when the peer tail keeps fp32 parameters on their owners only
+        (SNB_PEER_F16ONLY=1): non-owned chunks are zeroed in a copy and the copies summed; otherwise a plain clone."""
+        t = self.table.clone()
+        if self.peer is not None and self.peer_f16_only:
+            import torch.distributed as dist
+            t *= dp.owner_mask(self.n_table, self.peer.rank, self.peer.world, self.device)
+            dist.all_reduce(t)
+        return t
 
     def net_struct(self) -> SnbNet:
         return SnbNet(self.table_f16.data_ptr(), self.net.data_ptr(), self.meta, self.n_active)
@@ -186,7 +202,7 @@ class SDFModel:
         o, s = self._small_offsets(), self.small
         return {
             "sdf_network_fine": {
-                "encoding.params": self.table.clone(),
+                "encoding.params": self.gather_table(),
                 "lin0.bias": s[o["b0"]:o["v1"]].clone(), "lin0.weight_g": s[o["g0"]:o["b0"]].clone().view(H, 1),
                 "lin0.weight_v": s[o["v0"]:o["g0"]].clone().view(H, self.d_in),
                 "lin1.bias": s[o["b1"]:o["b1"] + 1].clone(), "lin1.weight_g": s[o["g1"]:o["g1"] + 1].clone().view(1, 1),
