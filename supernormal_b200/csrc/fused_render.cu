@@ -410,7 +410,21 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// kFast (experimental, SNB_RENDER_FAST=1; NOT yet validated on a GPU): approximate division / reciprocal square root / exp in the
+// render stage (2-ulp MUFU forms instead of the IEEE sequences: ~12 divisions, 5 square roots and 2 sigmoids per ray sample).  The stage
+// is issue-bound (56 % issue-active, profiles/r01_ncu_render_fused_kernel_v1.txt) and its parity bar is a tolerance (3e-3 relative on the
+// rendered normals), not bits.  The default instantiation <false> is the validated code, unchanged.
+template <bool F> __device__ __forceinline__ float fdiv_(float a, float b) { return F ? __fdividef(a, b) : a / b; }
+template <bool F> __device__ __forceinline__ float fsqrt_(float a) { return F ? (a > 0.f ? a * rsqrtf(a) : 0.f) : sqrtf(a); }
+template <bool F> __device__ __forceinline__ float fsigmoid_(float x) { return F ? __fdividef(1.f, 1.f + __expf(-x)) : sigmoidf_(x); }
+template <bool F> __device__ __forceinline__ float dist3_(float ax, float ay, float az, float bx, float by, float bz) {
+    if (!F) return dist3(ax, ay, az, bx, by, bz);
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return fsqrt_<true>(dx * dx + dy * dy + dz * dz);
+}
+
 // phase 1 of a chunk: load this (sample, ray), build its position, publish s0 / position for the neighbours
+template <bool F>
 __device__ __forceinline__ void pt_stage(Pt &p, const RayConst &rc, RenderSmem &sh, int buf, int k, int lane, bool valid, int s, int S,
                                          const snb_samples &sm, const float *__restrict__ sdf) {
     float t0 = 0.f, t1 = 1.f;
@@ -425,7 +439,8 @@ __device__ __forceinline__ void pt_stage(Pt &p, const RayConst &rc, RenderSmem &
         p.s0 = __ldg(p0);
         p.s1 = __ldg(p1);
     }
-    float t0k = __fdiv_rn(__fmul_rn(t0, rc.num), rc.den), t1k = __fdiv_rn(__fmul_rn(t1, rc.num), rc.den);
+    float t0k = F ? __fdividef(__fmul_rn(t0, rc.num), rc.den) : __fdiv_rn(__fmul_rn(t0, rc.num), rc.den);
+    float t1k = F ? __fdividef(__fmul_rn(t1, rc.num), rc.den) : __fdiv_rn(__fmul_rn(t1, rc.num), rc.den);
     p.dt = t1k - t0k;
     sh.s0[buf][k][lane] = p.s0;
     sh.px[buf][k][lane] = __fadd_rn(rc.o[0], __fmul_rn(rc.d[0], t0k));
@@ -434,23 +449,24 @@ __device__ __forceinline__ void pt_stage(Pt &p, const RayConst &rc, RenderSmem &
 }
 
 // phase 2 (after a CTA barrier): dfd normal (models/renderer.py:187-223) and NeuS alpha (:171-179)
+template <bool F>
 __device__ __forceinline__ void pt_finish(Pt &p, const RayConst &rc, const RenderSmem &sh, int buf, int k, int lane, bool valid, float inv_s) {
     const int r = k / 3, c = k % 3;
     const int kl = c > 0 ? k - 1 : k, kr = c < 2 ? k + 1 : k, ku = r > 0 ? k - 3 : k, kd = r < 2 ? k + 3 : k;
     const float x = sh.px[buf][k][lane], y = sh.py[buf][k][lane], z = sh.pz[buf][k][lane];
-    p.dl = dist3(x, y, z, sh.px[buf][kl][lane], sh.py[buf][kl][lane], sh.pz[buf][kl][lane]);
-    p.dr = dist3(sh.px[buf][kr][lane], sh.py[buf][kr][lane], sh.pz[buf][kr][lane], x, y, z);
-    p.du = dist3(x, y, z, sh.px[buf][ku][lane], sh.py[buf][ku][lane], sh.pz[buf][ku][lane]);
-    p.dd = dist3(sh.px[buf][kd][lane], sh.py[buf][kd][lane], sh.pz[buf][kd][lane], x, y, z);
+    p.dl = dist3_<F>(x, y, z, sh.px[buf][kl][lane], sh.py[buf][kl][lane], sh.pz[buf][kl][lane]);
+    p.dr = dist3_<F>(sh.px[buf][kr][lane], sh.py[buf][kr][lane], sh.pz[buf][kr][lane], x, y, z);
+    p.du = dist3_<F>(x, y, z, sh.px[buf][ku][lane], sh.py[buf][ku][lane], sh.pz[buf][ku][lane]);
+    p.dd = dist3_<F>(sh.px[buf][kd][lane], sh.py[buf][kd][lane], sh.pz[buf][kd][lane], x, y, z);
     const float sl = sh.s0[buf][kl][lane], sr = sh.s0[buf][kr][lane], su = sh.s0[buf][ku][lane], sd = sh.s0[buf][kd][lane];
-    float proj0 = (p.s1 - p.s0) / p.dt;
-    float proj1 = c == 0 ? (sr - p.s0) / p.dr : (c == 1 ? (sr - sl) / (p.dl + p.dr) : (p.s0 - sl) / p.dl);
-    float proj2 = r == 0 ? (sd - p.s0) / p.dd : (r == 1 ? (sd - su) / (p.dd + p.du) : (p.s0 - su) / p.du);
+    float proj0 = fdiv_<F>(p.s1 - p.s0, p.dt);
+    float proj1 = c == 0 ? fdiv_<F>(sr - p.s0, p.dr) : (c == 1 ? fdiv_<F>(sr - sl, p.dl + p.dr) : fdiv_<F>(p.s0 - sl, p.dl));
+    float proj2 = r == 0 ? fdiv_<F>(sd - p.s0, p.dd) : (r == 1 ? fdiv_<F>(sd - su, p.dd + p.du) : fdiv_<F>(p.s0 - su, p.du));
 #pragma unroll
     for (int a = 0; a < 3; ++a) p.g[a] = valid ? rc.vinv[3 * a] * proj0 + rc.vinv[3 * a + 1] * proj1 + rc.vinv[3 * a + 2] * proj2 : 0.f;
-    p.c = sigmoidf_(p.s0 * inv_s);
-    p.n = sigmoidf_(p.s1 * inv_s);
-    p.raw = (p.c - p.n + 1e-5f) / (p.c + 1e-5f);
+    p.c = fsigmoid_<F>(p.s0 * inv_s);
+    p.n = fsigmoid_<F>(p.s1 * inv_s);
+    p.raw = fdiv_<F>(p.c - p.n + 1e-5f, p.c + 1e-5f);
     p.alpha = valid ? fminf(fmaxf(p.raw, 0.f), 1.f) : 0.f;
 }
 
@@ -463,6 +479,7 @@ __device__ __forceinline__ void pt_weight(Pt &p, float &Tcarry, int lane) {
     p.w = p.alpha * p.T;
 }
 
+template <bool F>
 __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batch b, const float *__restrict__ net, snb_samples sm,
                                                                   const float *__restrict__ sdf, float normal_w, float mask_w, float eik_w,
                                                                   float *__restrict__ comp, float *__restrict__ wsum,
@@ -494,14 +511,14 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
     Pt p;
     for (int j0 = 0, buf = 0; j0 < n; j0 += kChunk, buf ^= 1) {
         const bool valid = j0 + lane < n;
-        pt_stage(p, rc, sh, buf, k, lane, valid, base + j0 + lane, S, sm, sdf);
+        pt_stage<F>(p, rc, sh, buf, k, lane, valid, base + j0 + lane, S, sm, sdf);
         __syncthreads();
-        pt_finish(p, rc, sh, buf, k, lane, valid, inv_s);
+        pt_finish<F>(p, rc, sh, buf, k, lane, valid, inv_s);
         pt_weight(p, Tc, lane);
         cn[0] += p.w * p.g[0]; cn[1] += p.w * p.g[1]; cn[2] += p.w * p.g[2];
         ws += p.w;
         if (valid) {
-            float nrm = sqrtf(p.g[0] * p.g[0] + p.g[1] * p.g[1] + p.g[2] * p.g[2]);
+            float nrm = fsqrt_<F>(p.g[0] * p.g[0] + p.g[1] * p.g[1] + p.g[2] * p.g[2]);
             eik += (nrm - 1.f) * (nrm - 1.f);
         }
     }
@@ -549,9 +566,9 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
         const bool valid = j0 + lane < n;
         const int s = base + j0 + lane;
         if (!single) {
-            pt_stage(p, rc, sh, buf, k, lane, valid, s, S, sm, sdf);
+            pt_stage<F>(p, rc, sh, buf, k, lane, valid, s, S, sm, sdf);
             __syncthreads();
-            pt_finish(p, rc, sh, buf, k, lane, valid, inv_s);
+            pt_finish<F>(p, rc, sh, buf, k, lane, valid, inv_s);
             pt_weight(p, Tc, lane);
         }
         float gw = dc3[0] * p.g[0] + dc3[1] * p.g[1] + dc3[2] * p.g[2] + dws;
@@ -559,9 +576,9 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
         float pin = warp_incl_sum(term, lane);
         float A = Ac - (pin - term);                         // sum over samples >= j of gw*w  (CS/render_weight.cu:323-338)
         Ac -= __shfl_sync(kFull, pin, 31);
-        float dalpha = (gw * p.T - A) / fmaxf(1.f - p.alpha, 1e-10f);
-        float nrm = sqrtf(p.g[0] * p.g[0] + p.g[1] * p.g[1] + p.g[2] * p.g[2]);
-        float ek = nrm > 0.f ? eik_scale * (nrm - 1.f) / nrm : 0.f;
+        float dalpha = fdiv_<F>(gw * p.T - A, fmaxf(1.f - p.alpha, 1e-10f));
+        float nrm = fsqrt_<F>(p.g[0] * p.g[0] + p.g[1] * p.g[1] + p.g[2] * p.g[2]);
+        float ek = nrm > 0.f ? (F ? __fdividef(eik_scale * (nrm - 1.f), nrm) : eik_scale * (nrm - 1.f) / nrm) : 0.f;
         float dg[3], q[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) dg[a] = p.w * dc3[a] + ek * p.g[a];
@@ -570,17 +587,17 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
         float ds0 = 0.f, ds1 = 0.f;
         if (p.raw >= 0.f && p.raw <= 1.f) {   // clip passes the gradient on the closed interval, like torch.clamp
             float ce = p.c + 1e-5f;
-            float dcdf = dalpha * p.n / (ce * ce), dndf = -dalpha / ce;
+            float dcdf = F ? __fdividef(dalpha * p.n, ce * ce) : dalpha * p.n / (ce * ce), dndf = F ? __fdividef(-dalpha, ce) : -dalpha / ce;
             float gc = p.c * (1.f - p.c), gn = p.n * (1.f - p.n);
             ds0 = dcdf * gc * inv_s;
             ds1 = dndf * gn * inv_s;
             if (valid) dinv += dcdf * gc * p.s0 + dndf * gn * p.s1;
         }
-        float ut = q[0] / p.dt;
+        float ut = fdiv_<F>(q[0], p.dt);
         ds1 += ut;
         ds0 -= ut;
-        float ux = q[1] / (c == 0 ? p.dr : (c == 1 ? p.dl + p.dr : p.dl));
-        float uy = q[2] / (r == 0 ? p.dd : (r == 1 ? p.dd + p.du : p.du));
+        float ux = fdiv_<F>(q[1], c == 0 ? p.dr : (c == 1 ? p.dl + p.dr : p.dl));
+        float uy = fdiv_<F>(q[2], r == 0 ? p.dd : (r == 1 ? p.dd + p.du : p.du));
         sh.ux[k][lane] = valid ? ux : 0.f;
         sh.uy[k][lane] = valid ? uy : 0.f;
         __syncthreads();
@@ -618,8 +635,13 @@ extern "C" int32_t snb_render_fused(const snb_patch_batch *b, const snb_net *net
     if (b->n_patches == 0) return SNB_OK;
     SNB_REQUIRE(sdf && comp && wsum && stats && b->normal_gt && b->mask, SNB_ERR_NULL, "render_fused: null buffer");
     SNB_REQUIRE((d_sdf0 == nullptr) == (d_sdf1 == nullptr), SNB_ERR_NULL, "render_fused: d_sdf0/d_sdf1 must both be given or both be null");
-    render_fused_kernel<<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
-                                                                              eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
+    static const int fast = getenv("SNB_RENDER_FAST") ? atoi(getenv("SNB_RENDER_FAST")) : 0;   // experimental, see fdiv_ above
+    if (fast)
+        render_fused_kernel<true><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
+                                                                                      eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
+    else
+        render_fused_kernel<false><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
+                                                                                       eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
     SNB_LAUNCH_CHECK("render_fused");
     return SNB_OK;
 }
