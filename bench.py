@@ -356,6 +356,9 @@ def main():
                         "how": "HostBatchFeeder: packed batch in pinned host memory -> one H2D copy per step on a copy stream (double-buffered), loss terms D2H every step into a pinned ring",
                         "loss_last": e2e_losses[-1]["loss"] if e2e_losses else None},
                 "kernels": prof}
+        if prof.get("avg_samples"):   # samples/s beside patch-rays/s, because samples per ray change along the schedule
+            line["patch_ray_samples_per_s"] = {"value": prof["avg_samples"] * 9 * world / (ms / K * 1e-3), "samples_per_ray": prof["avg_samples"] / tr.n_patches,
+                                               "note": "sample count averaged over the profiled steps right after the timed window"}
         if prof.get("dominant"):
             dk = prof["dominant"]
             traffic, traffic_note = None, None
