@@ -14,6 +14,8 @@ if [ "${1:-}" = "dp" ]; then
   done
   exit 0
 fi
+echo "== opt-in tests"; SNB_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k "peer_tail_world1" 2>&1 | grep -E "passed|failed|^FAILED|^E  " | head
+echo "== opt-in tests"; SNB_EXPERIMENTAL=1 python -m pytest tests -m gpu -q -k peer_tail_world1 2>&1 | grep -E "passed|failed|^FAILED|^E  " | head
 echo "== baseline"; python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^FAILED" | head
 echo "== SNB_RENDER_FAST=1"; SNB_RENDER_FAST=1 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^FAILED" | head
 echo "== SNB_OCC_MMA=1"; SNB_OCC_MMA=1 python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^FAILED" | head

@@ -4,6 +4,7 @@ renderer / fields / losses.  Tolerances: marching samples bit-exact; fp32 quanti
 (different summation orders, fp16-accumulated features are bit-identical on both sides by construction
 of the oracle's C path but the torch oracle accumulates them in fp32 -> 1e-3 on features)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -592,3 +593,54 @@ def test_checkpoint_resume_continues_training(cuda):
     assert a.buf.totals.tolist() == b.buf.totals.tolist()          # same parameters, grid and batch: same samples
     la, lb = a.loss_terms(), b.loss_terms()
     assert lb["loss"] == pytest.approx(la["loss"], rel=1e-4) and a.iter_step == b.iter_step == 21
+
+
+@pytest.mark.skipif(os.environ.get("SNB_EXPERIMENTAL") != "1", reason="written without GPU access at the end of round 1; enable with SNB_EXPERIMENTAL=1")
+@pytest.mark.parametrize("f16_only", [0, 1])
+def test_peer_tail_world1_equals_train_tail(cuda, f16_only):
+    """snb_train_tail_peer with a peer group of ONE rank (plain device memory stands in for the symmetric allocation): the
+    reduction over ranks, the broadcast and both in-kernel barriers degenerate to this GPU, so every buffer must come out
+    bit-identical to snb_train_tail -- for the validated variant and for the fp16-only / local-zeroing one."""
+    import ctypes as C
+    from supernormal_b200 import dp
+    from supernormal_b200._lib import call
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer, SnbPeerGroup, NET_FLOATS
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    tr = FusedTrainer(ds, dict(DILIGENT_CONF, batch_size=300, end_iter=200, increase_bindwidth_every=1), device=cuda)
+    for _ in range(5):
+        tr.train_step()
+    m = tr.model
+    batch, jitter = tr.sample_batch_device(5)
+    tr.forward_backward(batch, tr.step_size(5), jitter, lean=True)
+    names = ("flat", "grad", "exp_avg", "exp_avg_sq", "table_f16", "net", "net_grad")
+    snap = {k: getattr(m, k).clone() for k in names}
+    stats = tr.buf.stats.clone()
+    t, lr = 6, 3e-4
+
+    def restore():
+        for k in names:
+            getattr(m, k).copy_(snap[k])
+        tr.buf.stats.copy_(stats)
+
+    restore()
+    ctx = tr._ctx(batch, None)
+    call("snb_train_tail", C.byref(ctx), lr, t, 1.0, 0, None, 0, 0, 0, None)
+    torch.cuda.synchronize()
+    ref = {k: getattr(m, k).clone() for k in names}
+
+    restore()
+    m.grad[:NET_FLOATS] = snap["net_grad"]        # peer mode: the folded-weight gradient lives in flat_grad[0:2432)
+    flags = torch.zeros(dp.PEER_FLAG_WORDS, dtype=torch.int32, device=cuda)
+    counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+    one = lambda p: (C.c_void_p * dp.MAX_PEERS)(p, *([None] * (dp.MAX_PEERS - 1)))
+    pg = SnbPeerGroup(1, 0, one(m.flat.data_ptr()), one(m.grad.data_ptr()), one(m.table_f16.data_ptr()), one(flags.data_ptr()),
+                      counter.data_ptr(), f16_only)
+    ctx = tr._ctx(batch, None)
+    ctx.net_grad = m.grad.data_ptr()
+    call("snb_train_tail_peer", C.byref(ctx), C.byref(pg), lr, t, None, 0, 0, 0, None)
+    torch.cuda.synchronize()
+    assert flags[16].item() == 0 and counter.item() == 0 and flags[0].item() == t and flags[dp.MAX_PEERS].item() == t
+    for k in ("flat", "exp_avg", "exp_avg_sq", "table_f16", "net"):
+        assert torch.equal(getattr(m, k), ref[k]), k
+    assert (m.grad == 0).all()
