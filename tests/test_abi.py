@@ -40,3 +40,22 @@ def test_product_has_no_oracle_import():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every ctypes mirror of a struct in include/snb200.h has the size the C compiler gives it (gcc, same ABI as nvcc's host side)."""
+    import ctypes as C
+    import subprocess
+    from supernormal_b200 import _lib, trainer
+    pairs = {"snb_hashgrid_meta": _lib.HashGridMeta, "snb_net": trainer.SnbNet, "snb_patch_batch": trainer.SnbPatchBatch,
+             "snb_samples": trainer.SnbSamples, "snb_dataset": trainer.SnbDataset, "snb_batch_out": trainer.SnbBatchOut,
+             "snb_train_ctx": trainer.SnbTrainCtx, "snb_peer_group": trainer.SnbPeerGroup}
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "snb200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, ct in pairs.items():
+        assert int(out[name]) == C.sizeof(ct), (name, out[name], C.sizeof(ct))
