@@ -1,9 +1,10 @@
 """Host-side data-parallel plumbing (one process per GPU).  Pure torch / torch.distributed on whatever
 backend the process group uses (NCCL on the GPU box, gloo in the CPU tests): nothing here touches libsnb200.
 
-  * gradient exchange: one all-reduce (sum) over the LIVE prefix of the flat gradient buffer
-    [ MLP block | hash-table levels < n_active ] -- levels that are not active yet have exactly zero gradient on every
-    rank, so they are neither reduced nor swept by Adam;
+  * gradient exchange over the LIVE prefix of the flat gradient buffer [ MLP block | hash-table levels < n_active ] --
+    levels that are not active yet have exactly zero gradient on every rank, so they are neither reduced nor swept by
+    Adam.  Default on a GPU box: the peer-memory step tail (libsnb200's snb_train_tail_peer; PeerGroup below sets up the
+    symmetric allocation and the static chunk ownership); fallback / gloo tests: one all-reduce (sum);
   * patch sharding: rank r draws its own patches from the counter-based stream (seed + 7919 r, step) -- weak scaling,
     no data-path collective;
   * mesh extraction: x-slabs of the SDF lattice per rank (+1 halo plane), gathered and welded on rank 0.

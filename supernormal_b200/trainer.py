@@ -73,7 +73,7 @@ class SDFModel:
     weight-norm, Softplus(beta=100), input_concat, geometric init) + SingleVarianceNetwork
     (models/fields.py:133-139) in ONE flat fp32 buffer:  [ small | pad | hash table ]
         small = v0[64, d_in] | g0[64] | b0[64] | v1[64] | g1 | b1 | variance,   d_in = 3 + 2*n_levels
-    so that Adam and the data-parallel allreduce are single contiguous sweeps.  A persistent fp16 copy
+    so that Adam and the data-parallel gradient exchange are single contiguous sweeps.  A persistent fp16 copy
     of the table (what tiny-cuda-nn gathers from) is refreshed by the optimizer kernel."""
 
     def __init__(self, encoding_config: dict, bias: float = 0.6, variance_init: float = 0.5, seed: int = 1337, device="cuda",
@@ -366,9 +366,10 @@ def make_batch_struct(rays_o, rays_d, plane_n, near, far, v_inv, normal_gt, mask
 
 
 class FusedTrainer:
-    """Runner.train (exp_runner.py:147-210) on the fused kernels.  One process per GPU; with
-    torch.distributed initialised, gradients are all-reduced (sum) over NCCL before Adam and divided by
-    the world size (each rank draws its own patches: weak scaling)."""
+    """Runner.train (exp_runner.py:147-210) on the fused kernels.  One process per GPU; with world_size > 1 (torch.distributed
+    initialised) each rank draws its own patches (weak scaling) and the gradients of all ranks are summed, scaled by
+    1 / world_size and applied identically everywhere: inside the step-tail kernel over NVLink peer memory (snb_train_tail_peer:
+    peer loads, Adam state sharded by chunk owner, parameter broadcast), or by an NCCL all-reduce + replicated Adam with SNB_DP=nccl."""
 
     def __init__(self, dataset, conf: dict, device="cuda", seed: int = 0, samples_per_ray_cap: int = 320,
                  world_size: int = 1, rank: int = 0):
