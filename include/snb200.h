@@ -351,10 +351,13 @@ typedef struct snb_peer_group {
     void *table_f16[SNB_MAX_PEERS];
     uint32_t *flags[SNB_MAX_PEERS];
     uint32_t *counter;
-    int32_t table_f16_only; /* 0 (default, validated on 2 and 8 GPUs): owners broadcast fp32 parameters + fp16 copy and zero the
-                             * peers' gradient chunks.  1 (experimental, not yet validated on a GPU): owners broadcast the fp16
-                             * copy only (fp32 master parameters stay valid on the owner's chunks alone) and every rank zeroes
-                             * its own gradient range after the done barrier. */
+    int32_t table_f16_only; /* 0: owners broadcast fp32 parameters + fp16 copy and zero the peers' gradient chunks.  1 (what
+                             * FusedTrainer uses; validated on 2 GPUs, profiles/r02_dp_peer_check_n2_f16only1.json): owners
+                             * broadcast the fp16 copy only (fp32 master parameters stay valid on the owner's chunks alone) and
+                             * every rank zeroes its own gradient range after the done barrier. */
+    uint32_t epoch;         /* value the two in-kernel barriers wait for: must grow strictly from launch to launch of one peer
+                             * group, whatever the optimizer step count does (a resume rewinds step_count, not this).  0: use
+                             * step_count (a run that never rewinds). */
 } snb_peer_group;
 int32_t snb_train_tail_peer(const snb_train_ctx *h_ctx, const snb_peer_group *h_peers, float lr, int32_t step_count,
                             const snb_dataset *h_ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,

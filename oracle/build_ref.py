@@ -73,6 +73,30 @@ def build(verbose: bool = False) -> str | None:
     return out
 
 
+REF_MODELS = "/root/reference/models"
+MODELS_OUT = os.path.join(OUT_DIR, "models")
+MODEL_FILES = ("renderer", "fields")
+
+
+def build_models(verbose: bool = False) -> str | None:
+    """Byte-compile the reference's OWN models/renderer.py and models/fields.py, where they lie, into sourceless
+    oracle/_ref/models/*.pyc (a compiled artefact like the .so above: git-ignored, travels to the GPU box, no source copied into
+    the repo).  The `-m gpu` drop-in test executes this literal reference code on top of the product's nerfacc / tinycudann shims
+    (tests/test_reference_literal.py); oracle/ref_models.py loads it."""
+    if not os.path.isdir(REF_MODELS):
+        return MODELS_OUT if all(os.path.exists(os.path.join(MODELS_OUT, f + ".pyc")) for f in MODEL_FILES) else None
+    import py_compile
+    os.makedirs(MODELS_OUT, exist_ok=True)
+    for f in MODEL_FILES:
+        src, out = os.path.join(REF_MODELS, f + ".py"), os.path.join(MODELS_OUT, f + ".pyc")
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            py_compile.compile(src, cfile=out, dfile=f"<reference>/models/{f}.py", doraise=True,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            if verbose:
+                print("compiled", out)
+    return MODELS_OUT
+
+
 def load():
     """Import the built module (requires torch; returns None when unavailable)."""
     p = so_path()
@@ -89,3 +113,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(verbose=True))
+    print(build_models(verbose=True))

@@ -217,6 +217,7 @@ class CudaTrainer(T.Trainer):
         rm = conf["ray_marching"]
         self.slop = (math.log10(rm["start_step_size"]) - math.log10(rm["end_step_size"])) / conf["end_iter"]
         self.iter_step = 0
+        self._set_lr()      # exp_runner.py:125: update_learning_rate() before the first iteration -> step 0 runs at lr = 0
 
 
 def time_steps(tr: CudaTrainer, steps: int, warmup: int):

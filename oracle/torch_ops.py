@@ -431,7 +431,8 @@ class Trainer:
         self.opt = torch.optim.Adam(list(self.sdf.parameters()) + list(self.dev.parameters()), lr=conf["learning_rate"])
         rm = conf["ray_marching"]
         self.slop = (math.log10(rm["start_step_size"]) - math.log10(rm["end_step_size"])) / conf["end_iter"]
-        self.iter_step = 0  # NB: step 0 runs with Adam's constructor lr; the schedule starts after it (exp_runner.py:97,210)
+        self.iter_step = 0
+        self._set_lr()      # Runner.train calls update_learning_rate() before the loop (exp_runner.py:125): step 0 runs at lr = 0
 
     def _set_lr(self):
         f = lr_factor(self.iter_step, self.conf["warm_up_end"], self.conf["end_iter"], self.conf["learning_rate_alpha"])

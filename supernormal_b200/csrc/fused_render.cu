@@ -410,10 +410,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// kFast (experimental, SNB_RENDER_FAST=1; NOT yet validated on a GPU): approximate division / reciprocal square root / exp in the
-// render stage (2-ulp MUFU forms instead of the IEEE sequences: ~12 divisions, 5 square roots and 2 sigmoids per ray sample).  The stage
-// is issue-bound (56 % issue-active, profiles/r01_ncu_render_fused_kernel_v1.txt) and its parity bar is a tolerance (3e-3 relative on the
-// rendered normals), not bits.  The default instantiation <false> is the validated code, unchanged.
+// F = true (the only instantiation launched): approximate division / reciprocal square root / exp in the render stage (2-ulp MUFU
+// forms instead of the IEEE sequences: ~12 divisions, 5 square roots and 2 sigmoids per ray sample).  The stage is issue-bound (56 %
+// issue-active, profiles/r01_ncu_render_fused_kernel_v1.txt) and its parity bar is a tolerance (3e-3 relative on the rendered
+// normals), not bits.  Validated on a B200 in round 2 (all fused-vs-legacy / oracle tolerance tests green with it; 67 -> 48 us at
+// iteration 100, 41 -> 30 us at 1000, 84 -> 62 us at 4800: profiles/r02_variants_validation.txt); the IEEE instantiation was dropped.
 template <bool F> __device__ __forceinline__ float fdiv_(float a, float b) { return F ? __fdividef(a, b) : a / b; }
 template <bool F> __device__ __forceinline__ float fsqrt_(float a) { return F ? (a > 0.f ? a * rsqrtf(a) : 0.f) : sqrtf(a); }
 template <bool F> __device__ __forceinline__ float fsigmoid_(float x) { return F ? __fdividef(1.f, 1.f + __expf(-x)) : sigmoidf_(x); }
@@ -635,13 +636,8 @@ extern "C" int32_t snb_render_fused(const snb_patch_batch *b, const snb_net *net
     if (b->n_patches == 0) return SNB_OK;
     SNB_REQUIRE(sdf && comp && wsum && stats && b->normal_gt && b->mask, SNB_ERR_NULL, "render_fused: null buffer");
     SNB_REQUIRE((d_sdf0 == nullptr) == (d_sdf1 == nullptr), SNB_ERR_NULL, "render_fused: d_sdf0/d_sdf1 must both be given or both be null");
-    static const int fast = getenv("SNB_RENDER_FAST") ? atoi(getenv("SNB_RENDER_FAST")) : 0;   // experimental, see fdiv_ above
-    if (fast)
-        render_fused_kernel<true><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
-                                                                                      eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
-    else
-        render_fused_kernel<false><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
-                                                                                       eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
+    render_fused_kernel<true><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
+                                                                                  eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
     SNB_LAUNCH_CHECK("render_fused");
     return SNB_OK;
 }

@@ -44,113 +44,6 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_eval_kernel(int64_t n, 
     }
 }
 
-// ---- fused occupancy update on the warp-cooperative tensor-core evaluator (experimental: SNB_OCC_MMA=1, NOT yet validated on a GPU) ----
-// Same work list and arithmetic as sampler.cu:occgrid_update_kernel (NA/grid.py:197-239 + models/renderer.py:56-60): every cell during
-// warm-up, afterwards every occupied cell (thinned to ~num_cells/4) + num_cells/4 uniform random cells; one jittered point per visit;
-// occs[c] = max(decay * occs_prev[c], sigmoid(-80 sdf)).  The thread-per-point FMA evaluator of that kernel leaves lanes of unoccupied
-// cells idle and runs layer 0 on the FMA pipe; here every warp compacts its active items into a 64-entry shared-memory queue and
-// evaluates full batches of 32 with warp_sdf_mma (mma.sync TF32, the evaluator of sdf_eval_kernel).
-constexpr int kOccQueue = 64;
-constexpr size_t kOccSmemBytes = kFwdSmemBytes + sizeof(float4) * kFwdWarps * kOccQueue;
-
-__global__ void __launch_bounds__(32 * kFwdWarps, 4) occgrid_update_mma_kernel(snb_net net, LevelTable lt, int3 res, const float *__restrict__ roi,
-                                                                              int warmup, float decay, uint64_t seed, uint64_t step,
-                                                                              float *__restrict__ occs, const float *__restrict__ occs_prev,
-                                                                              const uint8_t *__restrict__ binary,
-                                                                              const unsigned long long *__restrict__ ws) {
-    extern __shared__ __align__(16) float smem[];
-    const FwdSmem sh = fwd_smem_setup(smem, net.net);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *queue = reinterpret_cast<float4 *>(smem + kMmaSmemFloats(kFwdWarps)) + warp * kOccQueue;   // (x, y, z, cell id bits)
-    const LevelCtx *s_lvl = lt.lv;
-    const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
-    const int64_t num_cells = (int64_t)res.x * res.y * res.z;
-    const int64_t n_uniform = warmup ? 0 : num_cells / 4;
-    const int64_t total = num_cells + n_uniform;
-    const uint2 key = make_uint2((uint32_t)seed ^ 0x0cc61d00u, (uint32_t)(seed >> 32));
-    float thin = 1.f;
-    if (!warmup) {
-        unsigned long long n_occ = ws[1];
-        if (n_occ > (unsigned long long)(num_cells / 4)) thin = (float)(num_cells / 4) / (float)n_occ;
-    }
-    const float lo[3] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2)}, hi[3] = {__ldg(roi + 3), __ldg(roi + 4), __ldg(roi + 5)};
-    int qn = 0;   // warp-uniform queue fill
-
-    auto drain = [&](int n) {   // evaluate the first n (<= 32) queued items; all lanes participate
-        const bool valid = lane < n;
-        const float4 it = valid ? queue[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float s = warp_sdf_mma<false, true>(valid, it.x, it.y, it.z, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, nullptr, lane);
-        if (valid) {
-            const int c = __float_as_int(it.w);
-            occs[c] = fmaxf(__fmul_rn(occs_prev[c], decay), sigmoidf_(-s * 80.f));
-        }
-    };
-
-    const int64_t warp_id = (int64_t)blockIdx.x * kFwdWarps + warp, n_warps = (int64_t)gridDim.x * kFwdWarps;
-    for (int64_t w0 = warp_id * 32; w0 < total; w0 += n_warps * 32) {
-        const int64_t w = w0 + lane;
-        bool active = w < total;
-        int64_t c = 0;
-        uint4 r = make_uint4(0u, 0u, 0u, 0u);
-        if (active) {
-            r = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)w, (uint32_t)(w >> 32) ^ 0x77u), key);
-            if (w < num_cells) {
-                c = w;
-                if (!warmup) {
-                    if (!binary[c]) active = false;
-                    else if (thin < 1.f) {
-                        uint4 r2 = philox4x32_10(make_uint4((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)w, 0x1234567u), key);
-                        if (u01(r2.x) >= thin) active = false;
-                    }
-                }
-            } else {
-                c = (int64_t)(r.w % (uint32_t)num_cells);
-            }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, active);
-        if (active) {
-            const int cz = (int)(c % res.z), cy = (int)((c / res.z) % res.y), cx = (int)(c / ((int64_t)res.z * res.y));
-            const int cc[3] = {cx, cy, cz}, rr[3] = {res.x, res.y, res.z};
-            const float rnd[3] = {u01(r.x), u01(r.y), u01(r.z)};
-            float x[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                float u = __fdiv_rn(__fadd_rn((float)cc[d], rnd[d]), (float)rr[d]);
-                x[d] = __fmaf_rn(u, __fsub_rn(hi[d], lo[d]), lo[d]);
-            }
-            queue[qn + __popc(m & ((1u << lane) - 1u))] = make_float4(x[0], x[1], x[2], __int_as_float((int)c));
-        }
-        qn += __popc(m);
-        __syncwarp();
-        if (qn >= 32) {
-            drain(32);
-            __syncwarp();
-            const float4 rest = lane < qn - 32 ? queue[32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-            if (lane < qn - 32) queue[lane] = rest;
-            qn -= 32;
-            __syncwarp();
-        }
-    }
-    if (qn > 0) drain(qn);
-}
-
-int32_t occgrid_update_mma_launch(const snb_net *net, int32_t rx, int32_t ry, int32_t rz, const float *roi, int32_t warmup, float ema_decay,
-                                  uint64_t seed, uint64_t step, float *occs, const float *occs_prev, const uint8_t *binary,
-                                  const void *workspace, snb_stream_t stream) {
-    SNB_REQUIRE((int64_t)rx * ry * rz < (1ll << 31), SNB_ERR_ARG, "occgrid_update (mma): cell ids must fit 31 bits");
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(occgrid_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOccSmemBytes);
-        configured = true;
-    }
-    occgrid_update_mma_kernel<<<kNumSMs * 8, 32 * kFwdWarps, kOccSmemBytes, S(stream)>>>(*net, make_level_table(net->meta), make_int3(rx, ry, rz), roi,
-                                                                                       warmup, ema_decay, seed, step, occs, occs_prev, binary,
-                                                                                       (const unsigned long long *)workspace);
-    SNB_LAUNCH_CHECK("occgrid_update_fused (mma)");
-    return SNB_OK;
-}
-
 // sdf and d sdf / d x in one pass (analytic normals, models/fields.py:107-119 without the autograd graph)
 constexpr size_t kGradSmemBytes = kFwdSmemBytes + sizeof(float) * kFwdWarps * 3 * 32 * kTsStride;
 

@@ -339,7 +339,7 @@ __device__ __forceinline__ void wait_flags(const uint32_t *flags, uint32_t *err,
     __syncthreads();
 }
 
-// kF16Only (experimental, snb_peer_group.table_f16_only; NOT yet validated on a GPU -- see DESIGN.md section 6): the owner keeps the fp32
+// kF16Only (snb_peer_group.table_f16_only, FusedTrainer's default since it was validated on 2 GPUs -- DESIGN.md section 6): the owner keeps the fp32
 // master parameters of its chunks to itself and broadcasts only the fp16 copy the forward gathers from, and every rank zeroes its own
 // gradient range after the done barrier instead of the owner zeroing it remotely: 2 instead of 14 bytes per owned parameter leave the GPU.
 template <bool kF16Only>
@@ -638,7 +638,7 @@ extern "C" int32_t snb_train_tail_peer(const snb_train_ctx *c, const snb_peer_gr
         pa.flags[r] = pgrp->flags[r];
     }
     pa.counter = pgrp->counter;
-    pa.epoch = (uint32_t)step_count;
+    pa.epoch = pgrp->epoch ? pgrp->epoch : (uint32_t)step_count;
     // one CTA per SM at most (every waiting CTA is resident): block 0 + sampler blocks + chunk blocks <= 148
     const int64_t n_chunks = cdiv(a.n_live / 4, (int64_t)kTailThreads);
     int64_t own_chunks = cdiv(n_chunks, (int64_t)pgrp->world);

@@ -4,9 +4,6 @@
 
 namespace snb {
 
-int32_t occgrid_update_mma_launch(const snb_net *net, int32_t rx, int32_t ry, int32_t rz, const float *roi, int32_t warmup, float ema_decay,
-                                  uint64_t seed, uint64_t step, float *occs, const float *occs_prev, const uint8_t *binary,
-                                  const void *workspace, snb_stream_t stream);
 int32_t adam_launch(int64_t n, float *param, float *grad, float *exp_avg, float *exp_avg_sq, void *param_f16, int64_t f16_start, float lr,
                     float beta1, float beta2, float eps, int32_t step_count, float grad_scale, snb_stream_t stream);
 
@@ -107,13 +104,10 @@ extern "C" int32_t snb_occgrid_update_fused(const snb_net *net, int32_t rx, int3
     SNB_REQUIRE(aligned(workspace, 8) && aligned(net->net, 16), SNB_ERR_ALIGN, "occgrid_update_fused: misaligned workspace/net");
     const int64_t n = (int64_t)rx * ry * rz;
     cudaMemcpyAsync(occs_prev, occs, sizeof(float) * n, cudaMemcpyDeviceToDevice, S(stream));
-    static const int use_mma = getenv("SNB_OCC_MMA") ? atoi(getenv("SNB_OCC_MMA")) : 0;   // experimental tensor-core evaluator (fused_sdf.cu)
-    if (use_mma) {
-        int32_t rc = occgrid_update_mma_launch(net, rx, ry, rz, roi, warmup, ema_decay, seed, step, occs, occs_prev, binary, workspace, stream);
-        if (rc) return rc;
-    } else
-        occgrid_update_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*net, make_level_table(net->meta), make_int3(rx, ry, rz), roi, warmup, ema_decay, seed, step, occs, occs_prev,
-                                                                binary, (const unsigned long long *)workspace);
+    // (a warp-queue + mma.sync evaluator for this sweep was measured in round 2 and dropped: no gain at <= 4 levels, ~20 us per step
+    // slower at 14 levels -- profiles/r02_variants_validation.txt)
+    occgrid_update_kernel<<<kNumSMs * 8, 256, 0, S(stream)>>>(*net, make_level_table(net->meta), make_int3(rx, ry, rz), roi, warmup, ema_decay, seed, step, occs, occs_prev,
+                                                            binary, (const unsigned long long *)workspace);
     cudaMemsetAsync(workspace, 0, 16, S(stream));
     occgrid_sum2_kernel<<<kNumSMs * 4, 256, 0, S(stream)>>>(n, occs, (double *)workspace);
     occgrid_threshold2_kernel<<<kNumSMs * 4, 256, 0, S(stream)>>>(n, occs, (const double *)workspace, occ_thre, binary,

@@ -65,7 +65,7 @@ class SnbTrainCtx(C.Structure):
 class SnbPeerGroup(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("param", C.c_void_p * dp.MAX_PEERS), ("grad", C.c_void_p * dp.MAX_PEERS),
                 ("table_f16", C.c_void_p * dp.MAX_PEERS), ("flags", C.c_void_p * dp.MAX_PEERS), ("counter", C.c_void_p),
-                ("table_f16_only", C.c_int32)]
+                ("table_f16_only", C.c_int32), ("epoch", C.c_uint32)]
 
 
 class SDFModel:
@@ -118,9 +118,11 @@ class SDFModel:
             self.peer_flags = pg.view(offs[3], dp.PEER_FLAG_WORDS, torch.int32)
             self.peer_counter = pg.view(offs[4], 1, torch.int32)
             self.net_grad = self.grad[:NET_FLOATS]    # the backward accumulates the folded-weight gradient where the peers read it
-            # experimental (not yet validated on a GPU): owners broadcast only the fp16 table copy; fp32 table parameters are then valid
-            # on the owner's chunks only and gather_table() reassembles them
-            self.peer_f16_only = os.environ.get("SNB_PEER_F16ONLY", "0") == "1"
+            # owners broadcast only the fp16 table copy the gathers read (2 instead of 14 bytes per owned parameter leave the GPU); fp32 table
+            # parameters are then valid on the owner's chunks only and gather_table() reassembles them.  Validated on 2 GPUs in round 2
+            # (profiles/r02_dp_peer_check_n2_f16only*.json: replicas bit-identical, trajectory equal to the NCCL path, full schedule 2.29 ->
+            # 2.16 s); SNB_PEER_F16ONLY=0 keeps the fp32-broadcast form (the one validated at N=8 in round 1) as the cross-check.
+            self.peer_f16_only = os.environ.get("SNB_PEER_F16ONLY", "1") == "1"
         else:
             self.flat = flat.to(self.device)
             self.grad = torch.zeros_like(self.flat)
@@ -320,6 +322,9 @@ class HostBatchFeeder:
     def submit(self, batch, jitter: Optional[torch.Tensor] = None) -> None:
         """Start the H2D copy of one host batch into the next device slot (returns immediately).  `batch` is a packed
         pinned buffer from new_host_batch()/pack() -- one cudaMemcpyAsync -- or an unpacked dict (+ jitter), packed here."""
+        if self.n_fed - self.n_run >= self.depth:
+            raise RuntimeError(f"HostBatchFeeder.submit: {self.n_fed - self.n_run} batches already queued (depth {self.depth}); "
+                               "call step() before submitting more -- the oldest slot has not been consumed")
         slot = self.n_fed % self.depth
         if self.n_fed >= self.depth:
             self.free[slot].synchronize()            # the step that used this slot `depth` submissions ago has finished
@@ -378,6 +383,11 @@ class FusedTrainer:
         self.n_patches = int(conf["batch_size"])
         assert int(conf["patch_size"]) == 3, "3x3 patches (config/diligent.conf:29)"
         assert conf.get("gradient_method", "dfd") == "dfd", "fused path implements dfd (the shipped default)"
+        # the kernels hard-wire what both shipped confs select; anything else must fail here, not train silently on other maths
+        if conf.get("loss_type", "l1") != "l2":     # exp_runner.py:61 defaults to 'l1' when the key is absent
+            raise NotImplementedError(f"fused trainer implements loss_type 'l2' (config/diligent.conf, own_objects.conf); got {conf.get('loss_type', 'l1')!r}")
+        if not float(conf.get("mask_weight", 0.0)) > 0.0:   # exp_runner.py:171-172: mask_weight == 0 switches to an all-ones mask
+            raise NotImplementedError("fused trainer implements mask_weight > 0 (mask from the dataset); mask_weight == 0 uses an all-ones mask in the reference")
         # data parallel: gradient reduction + sharded Adam + parameter broadcast inside ONE kernel over NVLink peer memory
         # (SNB_DP=peer, default) or NCCL allreduce + replicated Adam (SNB_DP=nccl, also the fallback when symmetric memory is unavailable)
         self.peer_mode = False
@@ -433,13 +443,15 @@ class FusedTrainer:
         self.occs_prev = torch.zeros(self.grid.num_cells, device=dv)
         self.occ_ws = torch.zeros(2, dtype=torch.float64, device=dv)
         self.iter_step = 0
-        self.lr = float(conf["learning_rate"])  # Adam's constructor value is what step 0 uses (exp_runner.py:97,210)
+        self.lr = float(conf["learning_rate"]) * self._lr_factor()   # Runner.train calls update_learning_rate() before the loop
+                                                                      # (exp_runner.py:125): step 0 runs at lr = 0, only Adam's moments move
         self.gen = torch.Generator(device=self.device).manual_seed(seed + rank)
         self.np_rng = np.random.RandomState(seed + rank)
         self.last_batch = None
         if self.peer_mode:
             import torch.distributed as dist
             self._peer_struct = self.model.peer_struct()
+            self._peer_epoch = 0
             torch.cuda.synchronize(self.device)
             dist.barrier()           # every rank's parameters are in place before anyone's first peer kernel
 
@@ -568,6 +580,10 @@ class FusedTrainer:
             return
         nxt = 1 - self._slot
         if self.peer_mode:   # reduction over NVLink peer memory, sharded Adam, parameter broadcast, fold, next batch: one launch
+            self._peer_epoch += 1                         # barrier epoch: a launch counter, NOT iter_step (load_state_dict rewinds that)
+            self._peer_struct.epoch = self._peer_epoch
+            if self._peer_epoch % 256 == 0:
+                self.check_peer_error()                   # a timed-out cross-GPU wait must stop the run, not train on unreduced gradients
             if presample_next:
                 call("snb_train_tail_peer", C.byref(ctx), C.byref(self._peer_struct), float(self.lr), t, C.byref(self.ds_struct), self.n_patches,
                      self.seed, self.iter_step + 1, C.byref(self._out_structs[nxt]))
@@ -610,10 +626,23 @@ class FusedTrainer:
         self.lr = self.conf["learning_rate"] * self._lr_factor()
 
     # -- checkpoint / resume -------------------------------------------------------
+    def _param_slices(self):
+        """(name, offset into the flat buffers, shape) in the order of `list(sdf_network.parameters()) + list(deviation_network.parameters())`
+        (exp_runner.py:86-91): tcnn's `params`, then per Linear `bias, weight_g, weight_v` (nn.utils.weight_norm re-registers g and v behind
+        the bias, models/fields.py:66-67), then `variance`.  These are the indices torch.optim.Adam.state_dict() numbers its state by."""
+        m = self.model
+        o = m._small_offsets()
+        return [("encoding.params", SMALL_PAD, (m.n_table,)),
+                ("lin0.bias", o["b0"], (H,)), ("lin0.weight_g", o["g0"], (H, 1)), ("lin0.weight_v", o["v0"], (H, m.d_in)),
+                ("lin1.bias", o["b1"], (1,)), ("lin1.weight_g", o["g1"], (1, 1)), ("lin1.weight_v", o["v1"], (1, H)),
+                ("variance", o["var"], ())]
+
     def state_dict(self) -> dict:
-        """What Runner.save_checkpoint stores (exp_runner.py:298-315: both networks, the optimizer, iter_step) under the
-        reference's keys, plus what it forgets and a resume needs: the occupancy grid (the reference restarts from an all-empty
-        grid after is_continue) and the number of active levels.  Collective in a data-parallel run with the peer-memory tail:
+        """What Runner.save_checkpoint stores (exp_runner.py:306-315): `sdf_network_fine`, `variance_network_fine`, `optimizer` =
+        torch.optim.Adam.state_dict() layout (`state[i] = {step, exp_avg, exp_avg_sq}` per parameter tensor in the reference's
+        parameter order, `param_groups`), `iter_step` -- the reference's own load_checkpoint (exp_runner.py:298-304) reads it.  Two
+        extra keys the reference forgets and a resume needs are added (the reference ignores unknown keys): `occupancy_grid` (the
+        reference restarts from an all-empty grid) and `n_active`.  Collective in a data-parallel run with the peer-memory tail:
         the table's Adam state is sharded by chunk owner and is summed back together (non-owned chunks are exactly zero)."""
         m = self.model
         ea, eas = m.exp_avg.clone(), m.exp_avg_sq.clone()
@@ -625,35 +654,67 @@ class FusedTrainer:
                 dist.all_reduce(t)
                 t[:SMALL_PAD] = small
         sd = m.reference_state_dict()
-        sd["optimizer"] = {"exp_avg": ea, "exp_avg_sq": eas, "step": self.iter_step}
+        state = {}
+        if self.iter_step > 0:                   # torch's Adam creates its state lazily at the first step()
+            for i, (_, off, shape) in enumerate(self._param_slices()):
+                n = int(np.prod(shape)) if len(shape) else 1
+                state[i] = {"step": torch.tensor(float(self.iter_step)), "exp_avg": ea[off:off + n].clone().view(shape),
+                            "exp_avg_sq": eas[off:off + n].clone().view(shape)}
+        group = dict(torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=float(self.conf["learning_rate"])).state_dict()["param_groups"][0])
+        group["lr"] = float(self.lr)             # exp_runner.py:278-279 writes the scheduled value into the group
+        group["params"] = list(range(len(self._param_slices())))
+        sd["optimizer"] = {"state": state, "param_groups": [group]}
         sd["iter_step"] = self.iter_step
         sd["n_active"] = m.n_active
         sd["occupancy_grid"] = {"occs": self.grid.occs.clone(), "binary": self.grid._binary.clone()}
         return sd
 
     @torch.no_grad()
+    def rebuild_occupancy(self) -> None:
+        """Occupancy grid from the current SDF alone (a reference checkpoint does not carry one): one all-cells sweep from an empty
+        grid, the form every_n_step uses while step < 256 (NA/grid.py:207-239)."""
+        self.grid.occs.zero_()
+        self.occs_prev.zero_()
+        self.grid._binary.zero_()
+        self.occ_ws.zero_()
+        self.update_occupancy(0)
+
+    @torch.no_grad()
     def load_state_dict(self, sd: dict) -> None:
-        """Resume: parameters, Adam moments, schedule position (step size, learning rate, active levels are functions of
-        iter_step) and the occupancy grid.  The patch stream is counter-based (seed, iteration), so a resumed run draws the
-        batches the uninterrupted run would have drawn."""
+        """Resume from state_dict() or from a checkpoint written by the reference's save_checkpoint: parameters, Adam moments,
+        schedule position (step size, learning rate and the number of active levels are functions of iter_step) and the occupancy
+        grid (rebuilt from the SDF when the checkpoint has none).  The patch stream is counter-based (seed, iteration), so a resumed
+        run draws the batches the uninterrupted run would have drawn."""
         m = self.model
         m.load_reference_state_dict(sd)
-        opt = sd["optimizer"]
-        m.exp_avg.copy_(opt["exp_avg"].to(self.device))
-        m.exp_avg_sq.copy_(opt["exp_avg_sq"].to(self.device))
+        m.exp_avg.zero_()
+        m.exp_avg_sq.zero_()
+        state = sd["optimizer"]["state"]
+        for i, (_, off, shape) in enumerate(self._param_slices()):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            n = int(np.prod(shape)) if len(shape) else 1
+            m.exp_avg[off:off + n] = st["exp_avg"].to(self.device, torch.float32).flatten()
+            m.exp_avg_sq[off:off + n] = st["exp_avg_sq"].to(self.device, torch.float32).flatten()
         if self.peer_mode:   # keep only the chunks this rank owns
             mine = dp.owner_mask(m.n_table, self.rank, self.world_size, self.device)
             m.exp_avg[SMALL_PAD:] *= mine
             m.exp_avg_sq[SMALL_PAD:] *= mine
         m.grad.zero_()
         self.iter_step = int(sd["iter_step"])
-        m.n_active = int(sd["n_active"])
-        self.lr = float(self.conf["learning_rate"]) * (self._lr_factor() if self.iter_step > 0 else 1.0)
-        self.grid.occs.copy_(sd["occupancy_grid"]["occs"].to(self.device))
-        self.grid._binary.copy_(sd["occupancy_grid"]["binary"].to(self.device))
-        self.occ_ws.zero_()     # workspace of the fused occupancy update: [sum of occs (f64) | number of occupied cells (u64)]
-        self.occ_ws.view(torch.int64)[1] = int(self.grid._binary.sum().item())
+        every = int(self.conf["increase_bindwidth_every"])
+        # exp_runner.py:158-159: one more level at every iteration with iter_step % every == 0, starting with iteration 0
+        m.n_active = int(sd["n_active"]) if "n_active" in sd else min((self.iter_step + every - 1) // every, m.n_levels)
+        self.lr = float(self.conf["learning_rate"]) * self._lr_factor()
         self._presampled = (-1, 0)
+        if "occupancy_grid" in sd:
+            self.grid.occs.copy_(sd["occupancy_grid"]["occs"].to(self.device))
+            self.grid._binary.copy_(sd["occupancy_grid"]["binary"].to(self.device))
+            self.occ_ws.zero_()     # workspace of the fused occupancy update: [sum of occs (f64) | number of occupied cells (u64)]
+            self.occ_ws.view(torch.int64)[1] = int(self.grid._binary.sum().item())
+        else:
+            self.rebuild_occupancy()
         if self.peer_mode:
             import torch.distributed as dist
             torch.cuda.synchronize(self.device)
@@ -675,6 +736,10 @@ class FusedTrainer:
         self.check_peer_error()
         st = self.buf.stats.cpu().tolist()
         tot = self.buf.totals.cpu().tolist()
+        if tot[2]:   # set by the compaction kernel when a sample list was clipped to its capacity (or by a failed tcgen05 wait)
+            import warnings
+            warnings.warn(f"FusedTrainer: sample capacity exceeded at iteration {self.iter_step - 1} (samples_per_ray_cap = "
+                          f"{self.buf.capacity // self.n_patches}); the step ran on truncated sample lists -- raise samples_per_ray_cap", RuntimeWarning)
         S = max(tot[0], 1)
         c = self.conf
         normal = st[1] / st[0]
