@@ -19,6 +19,8 @@ ENC = dict(otype="HashGrid", n_levels=6, n_features_per_level=2, log2_hashmap_si
 
 
 ENC16 = dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.4)
+# the BASELINE / config/diligent.conf:80-87 encoding itself: 14 levels, T = 2^19, base 32, scale 2^0.4 (11 872 000 parameters)
+ENC_DILIGENT = dict(otype="HashGrid", n_levels=14, n_features_per_level=2, log2_hashmap_size=19, base_resolution=32, per_level_scale=1.3195079107728942)
 
 
 def _conf(n_patches, grad="dfd", enc=None):
@@ -126,7 +128,8 @@ def test_sdf_eval_grad_argument_errors(cuda):
 
 
 @pytest.mark.parametrize("variance,cut_active,n_active,enc", [(0.3, False, 4, ENC), (0.75, True, 4, ENC), (0.3, False, 2, ENC), (0.3, False, 6, ENC),
-                                                              (0.3, False, 16, ENC16), (0.3, False, 9, ENC16)])
+                                                              (0.3, False, 16, ENC16), (0.3, False, 9, ENC16),
+                                                              (0.3, False, 3, ENC_DILIGENT), (0.3, False, 14, ENC_DILIGENT), (0.75, True, 14, ENC_DILIGENT)])
 def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active, enc):
     """The backward is the tcgen05 kernel (8-column tiles up to 4 active levels, 32-column tiles beyond; 16 levels is the maximum the
     kernels are compiled for).  test_fma_backward_cross_check reruns two cases on the FMA kernel (SNB_BWD_UMMA=0)."""
@@ -580,8 +583,11 @@ def test_checkpoint_resume_continues_training(cuda):
     sd = a.state_dict()
     assert {"sdf_network_fine", "variance_network_fine", "optimizer", "iter_step", "occupancy_grid"} <= set(sd)
     b = FusedTrainer(ds, conf, device=cuda)
-    b.load_state_dict({k: ({kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if isinstance(v, dict) else v)
-                       for k, v in sd.items()})   # through host memory, like torch.save / torch.load
+    import io
+    f = io.BytesIO()
+    torch.save(sd, f)                              # exp_runner.py:315
+    f.seek(0)
+    b.load_state_dict(torch.load(f, map_location="cpu"))   # exp_runner.py:299
     assert b.iter_step == 20 and b.model.n_active == a.model.n_active == 4 and b.lr == pytest.approx(a.lr, rel=1e-12)
     for name in ("flat", "exp_avg", "exp_avg_sq", "table_f16"):
         assert torch.equal(getattr(a.model, name), getattr(b.model, name)), name
@@ -595,9 +601,8 @@ def test_checkpoint_resume_continues_training(cuda):
     assert lb["loss"] == pytest.approx(la["loss"], rel=1e-4) and a.iter_step == b.iter_step == 21
 
 
-@pytest.mark.skipif(os.environ.get("SNB_EXPERIMENTAL") != "1", reason="written without GPU access at the end of round 1; enable with SNB_EXPERIMENTAL=1")
-@pytest.mark.parametrize("f16_only", [0, 1])
-def test_peer_tail_world1_equals_train_tail(cuda, f16_only):
+@pytest.mark.parametrize("f16_only,epoch", [(0, 0), (1, 0), (1, 77)])
+def test_peer_tail_world1_equals_train_tail(cuda, f16_only, epoch):
     """snb_train_tail_peer with a peer group of ONE rank (plain device memory stands in for the symmetric allocation): the
     reduction over ranks, the broadcast and both in-kernel barriers degenerate to this GPU, so every buffer must come out
     bit-identical to snb_train_tail -- for the validated variant and for the fp16-only / local-zeroing one."""
@@ -635,12 +640,83 @@ def test_peer_tail_world1_equals_train_tail(cuda, f16_only):
     counter = torch.zeros(1, dtype=torch.int32, device=cuda)
     one = lambda p: (C.c_void_p * dp.MAX_PEERS)(p, *([None] * (dp.MAX_PEERS - 1)))
     pg = SnbPeerGroup(1, 0, one(m.flat.data_ptr()), one(m.grad.data_ptr()), one(m.table_f16.data_ptr()), one(flags.data_ptr()),
-                      counter.data_ptr(), f16_only)
+                      counter.data_ptr(), f16_only, epoch)
     ctx = tr._ctx(batch, None)
     ctx.net_grad = m.grad.data_ptr()
     call("snb_train_tail_peer", C.byref(ctx), C.byref(pg), lr, t, None, 0, 0, 0, None)
     torch.cuda.synchronize()
-    assert flags[16].item() == 0 and counter.item() == 0 and flags[0].item() == t and flags[dp.MAX_PEERS].item() == t
+    ep = epoch or t      # the barrier epoch: the launch counter when given, else the optimizer step count
+    assert flags[16].item() == 0 and counter.item() == 0 and flags[0].item() == ep and flags[dp.MAX_PEERS].item() == ep
     for k in ("flat", "exp_avg", "exp_avg_sq", "table_f16", "net"):
         assert torch.equal(getattr(m, k), ref[k]), k
     assert (m.grad == 0).all()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_peer_tail_two_ranks_replicas_bit_identical(cuda):
+    """torchrun x2 of scripts/dp_peer_check.py: with the peer-memory tail (snb_train_tail_peer) every rank holds the same parameter /
+    fp16-table / folded-net bits after 1, 2 and 24 steps, the gradient range is zero after the step, and the trajectory equals the
+    NCCL all-reduce path's (same batches; fp32 summation order only)."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29677",
+           os.path.join(root, "scripts", "dp_peer_check.py"), "--every", "3", "--steps", "40"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["peer_mode"] == [True, False]
+    assert all(a and b for a, b in out["replicas_identical_peer_nccl"]) and all(out["replicas_identical_end"])
+    assert out["grad_zero_after_step"] and out["frac_params_apart_gt_1e-6"][0] == 0.0
+    assert out["loss_max_rel_diff"] < 1e-3 and out["n_active"] >= 8
+
+
+def test_checkpoint_interoperates_with_the_reference_format(cuda):
+    """exp_runner.py:298-315: a checkpoint is {sdf_network_fine, variance_network_fine, optimizer = torch.optim.Adam.state_dict(),
+    iter_step}.  (1) FusedTrainer.state_dict() loads into the reference's own objects -- the literal models/fields.py networks and a
+    torch.optim.Adam over `list(sdf_network.parameters()) + list(deviation_network.parameters())` (exp_runner.py:86-97) -- with equal
+    tensors; (2) a checkpoint written by those objects (no occupancy grid, no n_active) resumes a FusedTrainer: same parameters and Adam
+    moments, n_active derived from iter_step, occupancy grid rebuilt from the SDF."""
+    from oracle import ref_models as R
+    if not R.available():
+        pytest.skip("reference models unavailable")
+    from supernormal_b200 import nerfacc_api, tcnn_api
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer, SMALL_PAD
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    conf = dict(DILIGENT_CONF, batch_size=256, end_iter=200, increase_bindwidth_every=5, warm_up_end=10)
+    a = FusedTrainer(ds, conf, device=cuda)
+    for _ in range(12):
+        a.train_step()
+    sd = a.state_dict()
+    _, fields_mod = R.load(nerfacc_api, tcnn_api)
+    kw = dict(d_out=1, d_in=3, d_hidden=64, n_layers=1, skip_in=[-1], bias=0.6, geometric_init=True, weight_norm=True, input_concat=True)
+    sdf_net = fields_mod.SDFNetwork(**kw, encoding_config=conf["encoding"]).to(cuda)
+    var_net = fields_mod.SingleVarianceNetwork(init_val=0.5).to(cuda)
+    params = list(sdf_net.parameters()) + list(var_net.parameters())
+    opt = torch.optim.Adam(params, lr=conf["learning_rate"])
+    # (1) ours -> reference objects
+    sdf_net.load_state_dict(sd["sdf_network_fine"])
+    var_net.load_state_dict(sd["variance_network_fine"])
+    opt.load_state_dict(sd["optimizer"])
+    assert opt.param_groups[0]["lr"] == pytest.approx(a.lr)
+    m = a.model
+    for p_, (name, off, shape) in zip(params, a._param_slices()):
+        n = p_.numel()
+        assert tuple(p_.shape) == tuple(shape), name
+        assert torch.equal(p_.detach().flatten(), m.flat[off:off + n]), name
+        st = opt.state[p_]
+        assert float(st["step"]) == 12 and torch.equal(st["exp_avg"].flatten(), m.exp_avg[off:off + n]), name
+        assert torch.equal(st["exp_avg_sq"].flatten(), m.exp_avg_sq[off:off + n]), name
+    # (2) reference objects -> ours: what Runner.save_checkpoint writes
+    ckpt = {"sdf_network_fine": sdf_net.state_dict(), "variance_network_fine": var_net.state_dict(), "optimizer": opt.state_dict(), "iter_step": 12}
+    b = FusedTrainer(ds, conf, device=cuda)
+    b.load_state_dict(ckpt)
+    assert b.iter_step == 12 and b.model.n_active == a.model.n_active == 3 and b.lr == pytest.approx(a.lr)
+    for name in ("flat", "exp_avg", "exp_avg_sq", "table_f16"):
+        assert torch.equal(getattr(a.model, name), getattr(b.model, name)), name
+    # the grid was rebuilt from the SDF (all-cells sweep): it must cover what the trained grid marks occupied, up to the EMA's memory
+    assert b.grid.binary.any()
+    inter = (a.grid.binary & b.grid.binary).sum().item()
+    assert inter >= 0.9 * min(a.grid.binary.sum().item(), b.grid.binary.sum().item())
+    b.train_step()
+    assert math.isfinite(b.loss_terms()["loss"])
