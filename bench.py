@@ -31,6 +31,9 @@ UNIT = "patch-rays/s"
 WORKLOAD = "diligent.conf-shaped training: 20 views 612x512 synthetic sphere normals, 2048 patches x 3x3 rays/step, 14-level hash grid T=2^19, full schedule from random init"
 
 
+L2_RED_PEAK_GOPS = 195.2   # G reduction sectors/s, measured on this pool's B200 (profiles/r02_red_rate_microbench.txt)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -127,34 +130,37 @@ class ClockSampler:
                 "samples": len(sm), "window": where}
 
 
-def cpu_port_run(steps, warmup, n_patches=64, threads=None, budget_s=None):
-    """The oracle (PyTorch-CPU port of the reference operators) on a bounded sample of the workload."""
+CPU_CONFIG = ("BASELINE configs[0]: synthetic sphere normal maps, 20 views 612x512, 3x3 patches, 512 patches/batch, 16-level hash grid "
+              "(T=2^19, base 32), one training step fwd+bwd+Adam via the PyTorch-CPU expression of the operators (oracle/)")
+
+
+def cpu_port_run(steps=8, warmup=2, n_patches=512, n_levels=16, threads=None, budget_s=None):
+    """The oracle (PyTorch-CPU port of the reference operators) on BASELINE.json configs[0] as written: 512 patches x 9
+    rays, 16 levels, real occupancy grid with its every-8-iterations update INSIDE the timed steps (warm-ups are iterations 0-1, so with
+    >= 7 timed steps iteration 8 carries one update: exactly the 1-in-8 amortisation).  -> (patch-rays/s from the mean step, mean ms,
+    median ms, threads, sample description)."""
     from oracle import torch_ops as T
     from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     ds = SyntheticDataset(SyntheticScene(), device="cpu")
-    conf = dict(DILIGENT_CONF, batch_size=n_patches)
+    conf = dict(DILIGENT_CONF, batch_size=n_patches, encoding=dict(DILIGENT_CONF["encoding"], n_levels=n_levels))
     tr = T.Trainer(ds, conf, seed=0)
-    # bounded sample: the 2M-cell occupancy sweep of iteration 0 is replaced by its analytic result for the
-    # geometric-init sphere (occupied where sdf < ~0.03, i.e. r < 0.63); timed steps skip grid updates.
-    r = torch.arange(128).float().add(0.5).div(64).sub(1)
-    gx, gy, gz = torch.meshgrid(r, r, r, indexing="ij")
-    tr.renderer.occupancy_grid.binary = (gx ** 2 + gy ** 2 + gz ** 2).sqrt() < 0.63
-    tr.renderer.occupancy_grid.every_n_step = lambda *a, **k: None
-    tr.sdf.bindwidth = 0
     for _ in range(warmup):
         tr.step()
-    t0 = time.perf_counter()
-    done = 0
-    while done < steps:
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < steps:
+        t0 = time.perf_counter()
         tr.step()
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s:   # bounded sample: stop after the step that crosses the budget
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_all > budget_s:   # bounded sample: stop after the step that crosses the budget
             break
-    steps = done
-    dt = time.perf_counter() - t0
-    return n_patches * 9 * steps / dt, dt / steps * 1e3, threads, f"{steps} steps of {n_patches} patches x 9 rays (of 2048) at the start of the schedule, analytic initial occupancy grid, no grid updates in the timed steps"
+    mean_s, med_s = float(np.mean(times)), float(np.median(times))
+    n_upd = sum(1 for it in range(warmup, warmup + len(times)) if it % conf["ray_marching"]["occ_update_freq"] == 0)
+    sample = (f"{len(times)} steps (iterations {warmup}..{warmup + len(times) - 1} after {warmup} warm-ups) of {n_patches} patches x 9 rays, {n_levels} levels, "
+              f"{n_upd} occupancy-grid update(s) inside the timed steps; value from the mean step, median {med_s * 1e3:.0f} ms")
+    return n_patches * 9 / mean_s, mean_s * 1e3, med_s * 1e3, threads, sample
 
 
 def ref_cuda_path_run(dev, warmup, steps, backend="reference"):
@@ -199,16 +205,19 @@ def emit(line: dict):
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the reference has no CPU path of its own (nerfacc / tiny-cuda-nn are CUDA-only and tiny-cuda-nn is absent from the
+    image), so this arm times the oracle port on the host cores: K steps of BASELINE configs[0] (512 patches, 16 levels; ~1.5-3 s each),
+    or as many as fit into ~100 s."""
     if rank != 0:
         return
-    # each step = a 64-patch sample of the 2048-patch batch (~1 s on 16 cores); K steps, or as many as fit into ~100 s of CPU work
-    warm = max(1, min(args.warmup, 3))
-    v, ms, threads, sample = cpu_port_run(max(1, args.steps), warm, budget_s=100.0)
+    warm = max(2, min(args.warmup, 2))
+    v, ms, med, threads, sample = cpu_port_run(max(1, args.steps), warm, budget_s=100.0)
     steps = int(sample.split()[0])
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "steps_requested": args.steps,
             "warmup": warm,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference has no CPU path (nerfacc/tcnn are CUDA-only); this is the PyTorch-CPU port of its operators (oracle/)"},
+            "ms_per_step": ms, "ms_per_step_median": med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CPU_CONFIG, "note": "reference has no CPU path (nerfacc/tcnn are CUDA-only); this is the PyTorch-CPU port of its operators (oracle/); "
+                       "patch-rays/s is per patch ray, so the 512-patch CPU sample and the 2048-patch GPU batch are comparable per unit of work"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -226,6 +235,8 @@ def main():
                     help="diligent: BASELINE configs[1] (default, the headline); own_objects: configs[2] (36 views 1512x2016, own_objects.conf schedule)")
     ap.add_argument("--flush-l2", action="store_true", help="time every step separately and overwrite a 512 MB buffer between steps (cold L2)")
     ap.add_argument("--ref-cuda-steps", type=int, default=100, help="steps of the reference-shaped CUDA path timed beside ours at N=1 (0 = skip)")
+    ap.add_argument("--no-ttm", action="store_true", help="skip the time-to-mesh leg (full schedule + 512^3 extraction on a fresh trainer)")
+    ap.add_argument("--cont-steps", type=int, default=400, help="secondary timed window: this many further iterations right after the K timed ones (0 = skip)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -309,6 +320,29 @@ def main():
     ms = float(t.item())
     value = tr.n_patches * 9 * K * world / (ms * 1e-3)
     lt = tr.loss_terms()
+    # ---- secondary window: the schedule simply continues for a few hundred more iterations (a K of 20 is a 5 ms region) ----
+    cont = None
+    if args.cont_steps > 0 and not args.flush_l2:
+        clk2 = ClockSampler(local)
+        if rank == 0:
+            clk2.start()
+            time.sleep(0.05)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        clk2.mark_start()
+        c0.record()
+        for _ in range(args.cont_steps):
+            tr.train_step()
+        c1.record()
+        barrier()
+        clk2.mark_end()
+        clk2.stop()
+        tc = torch.tensor([c0.elapsed_time(c1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        cms = float(tc.item())
+        cont = {"iterations": [W + K, W + K + args.cont_steps], "steps": args.cont_steps, "ms_per_step": cms / args.cont_steps,
+                "value": tr.n_patches * 9 * args.cont_steps * world / (cms * 1e-3), "unit": UNIT, "clocks": clk2.summary() if rank == 0 else None}
 
     # ---- per-kernel timing of the dominant kernels (CUDA events on the launching stream) ----------
     prof = tr.profile_kernels(steps=min(50, K)) if hasattr(tr, "profile_kernels") else {}
@@ -342,10 +376,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = te.n_patches * 9 * Ke * world / (float(t.item()) * 1e-3)
 
+    # ---- time-to-mesh (BASELINE.json metric, second half): the FULL schedule from random init on a fresh trainer + 512^3 extraction
+    # (slab-sharded over the ranks), and the schedule-average throughput that goes with it -------------------------------------
+    ttm = None
+    if not args.no_ttm:
+        from supernormal_b200.runner import time_to_mesh
+        del te, feeder
+        torch.cuda.empty_cache()
+        barrier()
+        r = time_to_mesh(ds, dict(CONF), 512, device=dev, seed=0, evaluate=(args.workload == "diligent"))
+        r.pop("vertices", None)
+        r.pop("triangles", None)
+        tt = torch.tensor([r["train_s"], r["time_to_mesh_s"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        r["train_s"], r["time_to_mesh_s"] = float(tt[0]), float(tt[1])
+        ttm = r
+
     if rank == 0:
         peak, which = peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (TF32 dz in backward)",
+                "data": "synthetic",
                 "config": {"workload": workload, "patches_per_gpu": tr.n_patches, "parallelism": f"dp{world}",
                            "l2_policy": ("flushed: 512 MB overwritten between steps, every step timed separately with CUDA events" if args.flush_l2 else
                                          "not flushed: a training run is a dependent chain of steps -- parameters are rewritten and patches are new random draws every step, "
@@ -356,6 +409,17 @@ def main():
                         "how": "HostBatchFeeder: packed batch in pinned host memory -> one H2D copy per step on a copy stream (double-buffered), loss terms D2H every step into a pinned ring",
                         "loss_last": e2e_losses[-1]["loss"] if e2e_losses else None},
                 "kernels": prof}
+        if cont:
+            line["continuation"] = cont
+        if ttm:
+            n_it = ttm["iters"]
+            line["time_to_mesh"] = {"value": ttm["time_to_mesh_s"], "unit": "s", "train_s": ttm["train_s"], "mesh_s": ttm["mesh_s"], "iters": n_it,
+                                    "mesh_resolution": ttm["resolution"], "n_vertices": ttm.get("n_vertices"), "n_triangles": ttm.get("n_triangles"),
+                                    "what": "wall clock from the first iteration of a fresh trainer to the mesh (vertices / faces) in host memory: end_iter training "
+                                            "iterations + extract_geometry(512), slab-sharded over the ranks",
+                                    **{k: ttm[k] for k in ("chamfer_mm", "fscore", "radius_mean", "mae_allview", "mae_testview") if k in ttm}}
+            line["schedule_avg"] = {"value": tr.n_patches * 9 * n_it * world / ttm["train_s"], "unit": UNIT, "ms_per_step": ttm["train_s"] / n_it * 1e3,
+                                    "what": "whole-schedule average (all levels come live along the way); host wall clock around the full training loop"}
         if prof.get("avg_samples"):   # samples/s beside patch-rays/s, because samples per ray change along the schedule
             line["patch_ray_samples_per_s"] = {"value": prof["avg_samples"] * 9 * world / (ms / K * 1e-3), "samples_per_ray": prof["avg_samples"] / tr.n_patches,
                                                "note": "sample count averaged over the profiled steps right after the timed window"}
@@ -372,6 +436,17 @@ def main():
                                 "avg_us": dk["us"],
                                 "note": "the step's kernels are latency / issue / L2-atomic bound at 2048 patches per GPU (DESIGN.md section 5); the only HBM-streaming "
                                         "kernel is the Adam sweep inside the step-tail kernel (snb_train_tail in kernels.hbm_model)"}
+            # second yardstick for the same kernel: its table scatter is bound by the L2 reduction path, not by HBM.  Peak = measured
+            # red.global.add.v2.f32 rate into an L2-resident 34 MB table (scripts/micro/red_rate.cu, profiles/r02_red_rate_microbench.txt:
+            # 97-100 reduction sectors per clock chip-wide, whatever the operand width).  Achieved = ALGORITHMIC corner updates (8 per point
+            # and live level) per second; the kernel merges same-cell neighbours before it issues, so the issued sector count is lower.
+            hm = prof.get("hbm_model", {}).get(dk["name"], {})
+            if hm.get("l2_useful_bytes"):
+                upd = hm["l2_useful_bytes"] / 8.0           # 8 B (one float2) per corner update
+                gops = upd / (dk["us"] * 1e-6) / 1e9
+                line["roofline_l2_reduction"] = {"bound": "l2-reduction", "kernel": dk["name"], "achieved": gops, "peak": L2_RED_PEAK_GOPS, "unit": "G corner updates/s vs G red sectors/s",
+                                                 "frac": gops / L2_RED_PEAK_GOPS, "corner_updates_per_launch": upd, "avg_us": dk["us"],
+                                                 "peak_source": "measured: profiles/r02_red_rate_microbench.txt (red.v2.f32, 33.6 MB table, 32 warps/SM)"}
         if Kr > 0:
             ours_ms = ev0.elapsed_time(evr) / Kr
             for backend, key in (("reference", "reference_cuda_path"), ("dropin", "dropin_api_path")):
@@ -384,8 +459,9 @@ def main():
                         r["ours_ms_per_step_same_window"] = ours_ms
                     line[key] = r
         if world == 1 and not args.no_cpu:
-            v, cms, threads, sample = cpu_port_run(3, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": cms}
+            v, cms, cmed, threads, sample = cpu_port_run(8, 2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": cms,
+                                    "ms_per_step_median": cmed, "config": CPU_CONFIG}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

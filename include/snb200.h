@@ -211,6 +211,9 @@ int32_t snb_sdf_eval(int64_t n, const float *x, const snb_net *h_net, int32_t mo
  * rounded to TF32 by the tensor core), fp32 accumulate.  K % 8 == 0, K <= 128, N in {32, 64}.  err (device i32) is set to 1 if the
  * MMA never signalled completion. */
 int32_t snb_umma_selftest(const float *A, const float *B, float *D, int32_t K, int32_t N, int32_t *err, snb_stream_t stream);
+/* same, with the A tile in the padded K-major layout (leading-dimension byte offset lbo_a = 128 or 192, csrc/umma.cuh) */
+int32_t snb_umma_selftest_lbo(const float *A, const float *B, float *D, int32_t K, int32_t N, int32_t lbo_a, int32_t *err,
+                              snb_stream_t stream);
 /* SDF and its analytic gradient d sdf / d x in ONE pass (forward-mode through encode + MLP on the tensor cores):
  * what SDFNetwork.gradient (models/fields.py:107-119) returns for `ad` normals (models/renderer.py:225-226, :345),
  * without the autograd double pass.  sdf: f32[n] or null; grad: f32[n,3]. */
@@ -244,6 +247,17 @@ int32_t snb_render_fused(const snb_patch_batch *h_batch, const snb_net *h_net, c
 int32_t snb_sdf_bwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
                           const void *feats, const float *d_sdf0, const float *d_sdf1, float *table_grad,
                           float *net_grad, snb_stream_t stream);
+/* The same backward with a caller-provided device workspace.  With more than 4 active levels and a workspace of at least
+ * snb_sdf_bwd_workspace_bytes(...) the work is split into two launches: (1) the tcgen05 MLP backward writes d loss / d features
+ * ([level][ray][sample] float2) and the point positions into the workspace, (2) a high-occupancy scatter kernel adds them to
+ * table_grad with the trilinear weights, merging contributions to the same grid cell in shared memory first and issuing the
+ * reductions corner-major so that x-neighbour corners share one L2 sector request (profiles/r02_red_rate_microbench.txt: the L2
+ * retires ~97 reduction SECTORS per clock whatever their width).  workspace == NULL (or too small, or <= 4 active levels): the
+ * single fused kernel of snb_sdf_bwd_patch.  Same results up to fp32 summation order. */
+int64_t snb_sdf_bwd_workspace_bytes(int32_t n_levels, int64_t capacity, int64_t end_capacity);
+int32_t snb_sdf_bwd_patch_ws(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                             const void *feats, const float *d_sdf0, const float *d_sdf1, float *table_grad,
+                             float *net_grad, void *workspace, int64_t workspace_bytes, snb_stream_t stream);
 /* Un-fold net_grad into gradients of (v,g,b,variance) (weight_norm / exp backward), in `small` layout. */
 int32_t snb_unfold_grads(int32_t n_levels, const float *small, const float *net_grad, const float *stats,
                          float *small_grad, snb_stream_t stream);
@@ -265,7 +279,8 @@ typedef struct snb_dataset { /* tensors Dataset.__init__ leaves on the device, m
     const float *masks;          /* [n_images,H,W] */
     const float *intrinsics_inv; /* [n_images,4,4] */
     const float *pose;           /* [n_images,4,4] camera-to-world */
-    const float *v_inverse;      /* [n_images,H,W,3,3] */
+    const float *v_inverse;      /* [n_images,H,W,3,3] (Dataset.V_inverse_all), or NULL: computed in closed form from pose and
+                                  * the pixel's camera-frame direction (no 36 B/pixel table; models/dataset_loader.py:114-137) */
     const int32_t *train_ids;    /* [n_train] view ids to sample from (exclude_views removed) */
 } snb_dataset;
 
@@ -305,6 +320,8 @@ typedef struct snb_train_ctx { /* everything one training iteration touches; all
     const float *roi;         /* [6] */
     const uint8_t *grid_binary;
     int32_t res_x, res_y, res_z;
+    void *bwd_workspace;      /* snb_sdf_bwd_patch_ws workspace (may be null: single-kernel backward) */
+    int64_t bwd_workspace_bytes;
 } snb_train_ctx;
 
 /* prep_net -> march_visible -> compact -> sdf_fwd_patch -> render_fwd -> patch_loss -> render_bwd ->

@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float sp, sg;
-                    softplus100_both(z[i], sp, sg);
+                    softplus100_both_lg2(z[i], sp, sg);
                     hact[c0 + i] = dsdf * sp;
                     dzv[i] = __uint_as_float(to_tf32(dsdf * s_w1[c0 + i] * sg));
                 }
@@ -635,6 +635,408 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
     if (warp == 0) umma::tmem_dealloc(tmem, kBwdTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// MLP backward of the split form (more than 4 live levels): same contractions as sdf_bwd_patch_umma_kernel<32>, no scatter
+// ---------------------------------------------------------------------------------------------
+// CTA = 256 threads on ONE 128-point tile: warps w and w + 4 share TMEM lanes 32 (w & 3) .. + 31 (a warp may touch the lane
+// quarter warp_id % 4) and split the 64 hidden units / the 16 level slots between them, i.e. TWO threads per point.  The
+// thread-per-point kernel above keeps 64 pre-activations + 64 dz in one thread (163 registers, 8 warps per SM: 12 % of the warp
+// slots, 33 % issue-active -- profiles/r02_ncu_bwd_split_v1_it4800.txt); halving the per-thread slice doubles the resident warps at the
+// same shared-memory footprint and halves every dependent chain (softplus block, transpose-reduce, weight-gradient MMAs).
+//   half 0 (warps 0-3): decodes the point, stages feature slots 0..15 + position columns, hidden units 0..31, levels 0..7 of the output
+//   half 1 (warps 4-7): stages feature slots 16..31, hidden units 32..63, levels 8..15
+// Output (instead of the table scatter): ws_dfeat[(level * 9 + ray) * qcap + q] = d loss / d feature (float2), ws_pos[ray * qcap + q]
+// = (x, y, z, live) -- consumed by hash_scatter_kernel.
+constexpr int kMlpThreads = 256;
+
+// v[32] per lane -> lane l ends with the warp sum of v[l] in v[0]
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, half = 16; off >= 1; off >>= 1, half >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            float send = up ? v[i] : v[i + half];
+            float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// LBO: leading-dimension byte offset of the two point tiles (X1 and dz): 192 = padded cores, conflict-free fragment loads in (4)
+template <int LBO>
+constexpr size_t mlp_smem_bytes() {
+    return umma::tile_bytes(64, BwdCfg<32>::kK1) * 2 + umma::tile_bytes(BwdCfg<32>::kN2, 64) + umma::tile_bytes_lbo<LBO>(128, BwdCfg<32>::kK1) +
+           umma::tile_bytes_lbo<LBO>(128, 64);
+}
+
+template <int LBO>
+__global__ void __launch_bounds__(kMlpThreads, 2) sdf_bwd_mlp_umma_kernel(snb_patch_batch b, snb_net net, snb_samples sm,
+                                                                          const __half2 *__restrict__ feats,
+                                                                          const float *__restrict__ d_sdf0,
+                                                                          const float *__restrict__ d_sdf1, float *__restrict__ net_grad,
+                                                                          int *__restrict__ err_flag, float2 *__restrict__ ws_dfeat,
+                                                                          float4 *__restrict__ ws_pos, int64_t qcap) {
+    constexpr int KF = 32;
+    using Cfg = BwdCfg<KF>;
+    constexpr int kK1 = Cfg::kK1, kColXhi = Cfg::kColXhi, kColXlo = Cfg::kColXlo, kColOne = Cfg::kColOne, kN2 = Cfg::kN2, kNMT = Cfg::kNMT;
+    constexpr uint32_t kBwdTmemCols = Cfg::kTmemCols;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_z, bar_u;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_w1[kH];
+    uint8_t *b1hi = smem_raw, *b1lo = b1hi + umma::tile_bytes(64, kK1), *b2 = b1lo + umma::tile_bytes(64, kK1);
+    uint8_t *a1 = b2 + umma::tile_bytes(kN2, 64), *a2 = a1 + umma::tile_bytes_lbo<LBO>(128, kK1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp >> 2, row = 32 * (warp & 3) + lane;      // this thread's point (row of the tiles, TMEM lane) and its half
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t L = net.meta.n_levels, n_active = net.n_active;
+
+    // ---- one-time staging: weights (TF32 hi / lo), TMEM, barriers
+    {
+        const float *W = net.net;
+        for (int e = tid; e < 64 * kK1; e += kMlpThreads) {
+            const int h = e / kK1, k = e % kK1;
+            float w = 0.f;
+            bool lo_zero = false;
+            if (k < KF) w = __ldg(W + kOffW0T + (3 + k) * kH + h);
+            else if (k < kColXlo) w = __ldg(W + kOffW0T + (k - kColXhi) * kH + h);
+            else if (k < kColOne) { w = __ldg(W + kOffW0T + (k - kColXlo) * kH + h); lo_zero = true; }   // x_lo * W_lo is below 2^-22
+            else if (k == kColOne) w = __ldg(W + kOffB0 + h);
+            const float hi = __uint_as_float(to_tf32(w));
+            *reinterpret_cast<float *>(b1hi + umma::kmajor_off(h, k, kK1)) = hi;
+            *reinterpret_cast<float *>(b1lo + umma::kmajor_off(h, k, kK1)) = lo_zero ? 0.f : __uint_as_float(to_tf32(w - hi));
+        }
+        for (int e = tid; e < kN2 * 64; e += kMlpThreads) {
+            const int j = e / 64, h = e % 64;
+            *reinterpret_cast<float *>(b2 + umma::kmajor_off(j, h, 64)) = j < KF ? __uint_as_float(to_tf32(__ldg(W + kOffW0T + (3 + j) * kH + h))) : 0.f;
+        }
+        if (tid < kH) s_w1[tid] = __ldg(W + kOffW1 + tid);
+        if (warp == 0) umma::tmem_alloc(&s_tmem, kBwdTmemCols);
+        if (tid == 0) { umma::mbar_init(&bar_z, 1); umma::mbar_init(&bar_u, 1); }
+        umma::fence_smem_to_async_proxy();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    }
+    const uint32_t tmem = s_tmem;
+    const uint32_t tmem_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const uint32_t a1_addr = umma::smem_u32(a1), a2_addr = umma::smem_u32(a2);
+    const uint32_t b1hi_addr = umma::smem_u32(b1hi), b1lo_addr = umma::smem_u32(b1lo), b2_addr = umma::smem_u32(b2);
+    const uint32_t idesc_z = umma::idesc_tf32(128, 64), idesc_u = umma::idesc_tf32(128, kN2);
+
+    const int S = sm.totals[0], E = sm.totals[1];
+    const int64_t Q = (int64_t)S + E;                            // sample starts + own interval ends; point p = 9 q + k
+    // tile = kTileQ consecutive q x 9 rays, ray-major over the rows (row r -> ray r / kTileQ, q = q0 + r % kTileQ): the layout
+    // hash_scatter_kernel reads back along q
+    constexpr int kTileQ = 14;
+    const int tk = row / kTileQ, tj = row % kTileQ;
+    const int n_feat_steps = (int)(2 * n_active + 7) >> 3;     // feature k-steps of (1) that can be non-zero
+    // (4): warp w owns hidden n-tile w (8 columns) and all kNMT 16-row column tiles of X1
+    float wacc[kNMT][4];
+#pragma unroll
+    for (int i = 0; i < kNMT; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wacc[i][c] = 0.f;
+    // dW1 partial sums of this thread's point rows over all its tiles, per hidden unit of its half (transpose-reduced over the warp once,
+    // at the end: a per-tile reduction costs 31 shuffles + ~90 selects / adds per thread and tile)
+    float accH[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) accH[i] = 0.f;
+    float accB1 = 0.f;
+    uint32_t phase = 0;
+    bool failed = false;
+
+    // point data one tile ahead in registers (see sdf_bwd_patch_umma_kernel): half 0 carries the position, each half its 8 level slots
+    struct TileRegs {
+        bool valid;
+        float dsdf, px, py, pz;
+        __half2 f[8];
+    };
+    auto fetch = [&](int64_t q0, TileRegs &o) {
+        const int64_t q = q0 + tj, p = q * SNB_PATCH + tk;
+        o.valid = tk < SNB_PATCH && q < Q;
+        o.dsdf = 0.f;
+        o.px = o.py = o.pz = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) o.f[l] = __float2half2_rn(0.f);
+        if (o.valid) {
+            int s;
+            bool is_end;
+            if (half == 0) {
+                const PointRef r = decode_point(p, S, b, sm);
+                o.px = r.px; o.py = r.py; o.pz = r.pz;
+                s = r.s; is_end = r.is_end;
+            } else {
+                is_end = q >= S;
+                s = is_end ? __ldg(sm.slot_sample + (q - S)) : (int)q;
+            }
+            if (!is_end) {
+                o.dsdf = __ldg(d_sdf0 + (int64_t)s * SNB_PATCH + tk);
+                // this start also served as the previous interval's end when that interval had no own end query
+                if (s > 0 && __ldg(sm.end_slot + s - 1) < 0) o.dsdf += __ldg(d_sdf1 + (int64_t)(s - 1) * SNB_PATCH + tk);
+            } else {
+                o.dsdf = __ldg(d_sdf1 + (int64_t)s * SNB_PATCH + tk);
+            }
+            const __half2 *fr = feats + p * L + 8 * half;
+#pragma unroll
+            for (int l = 0; l < 8; ++l)
+                if (8 * half + l < (int)n_active) o.f[l] = fr[l];
+        }
+    };
+    TileRegs nxt;
+    fetch((int64_t)blockIdx.x * kTileQ, nxt);
+
+    for (int64_t q0 = (int64_t)blockIdx.x * kTileQ; q0 < Q; q0 += (int64_t)gridDim.x * kTileQ) {
+        // ---- stage row `row` of X1: this half's 16 feature columns; half 0 also the position columns
+        const bool valid = nxt.valid;
+        const float dsdf = nxt.dsdf;
+        const float px = nxt.px, py = nxt.py, pz = nxt.pz;
+        {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // chunks of 4 feature columns (2 levels each)
+                const float2 f0 = __half22float2(nxt.f[2 * q]), f1 = __half22float2(nxt.f[2 * q + 1]);
+                *reinterpret_cast<float4 *>(a1 + umma::kmajor_off_lbo<LBO>(row, 16 * half + 4 * q, kK1)) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            }
+            if (half == 0) {
+                const float xh = __uint_as_float(to_tf32(px)), yh = __uint_as_float(to_tf32(py)), zh = __uint_as_float(to_tf32(pz));
+                const float xl = __uint_as_float(to_tf32(px - xh)), yl = __uint_as_float(to_tf32(py - yh)), zl = __uint_as_float(to_tf32(pz - zh));
+                *reinterpret_cast<float4 *>(a1 + umma::kmajor_off_lbo<LBO>(row, KF, kK1)) = make_float4(xh, yh, zh, xl);
+                *reinterpret_cast<float4 *>(a1 + umma::kmajor_off_lbo<LBO>(row, KF + 4, kK1)) = make_float4(yl, zl, 1.f, 0.f);
+            }
+        }
+        fetch(q0 + (int64_t)gridDim.x * kTileQ, nxt);      // next tile's loads are in flight from here on
+        umma::fence_smem_to_async_proxy();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+
+        // ---- (1) Z = X1 B1^T
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int s = 0; s < kK1 / 8; ++s) {
+                if (s < KF / 8 && s >= n_feat_steps) continue;   // all-zero feature columns
+                const uint64_t ad = umma::kmajor_desc_lbo<LBO>(a1_addr + 2u * LBO * s, kK1);
+                umma::mma_tf32(tmem, ad, umma::kmajor_desc(b1hi_addr + 256u * s, kK1), idesc_z, acc);
+                umma::mma_tf32(tmem, ad, umma::kmajor_desc(b1lo_addr + 256u * s, kK1), idesc_z, 1);
+                acc = 1;
+            }
+            umma::commit(&bar_z);
+        }
+        if (!umma::mbar_wait(&bar_z, phase)) failed = true;
+        umma::fence_after_sync();
+
+        // ---- (2) dz, dW1 / db1 for this thread's 32 hidden units
+        {
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                const int h0 = 32 * half + c0;
+                float z[16];
+                umma::tmem_ld16(tmem_lane + (uint32_t)h0, z);
+                umma::tmem_ld_wait();
+                float dzv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float sp, sg;
+                    softplus100_both_lg2(z[i], sp, sg);
+                    accH[c0 + i] = fmaf(dsdf, sp, accH[c0 + i]);
+                    dzv[i] = __uint_as_float(to_tf32(dsdf * s_w1[h0 + i] * sg));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4 *>(a2 + umma::kmajor_off_lbo<LBO>(row, h0 + 4 * q, 64)) = make_float4(dzv[4 * q], dzv[4 * q + 1], dzv[4 * q + 2], dzv[4 * q + 3]);
+            }
+            if (half == 0) {
+                float ds = dsdf;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+                accB1 += ds;
+            }
+        }
+        umma::fence_smem_to_async_proxy();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+
+        // ---- (3) U = dz W0feat  (async on the tensor pipe)
+        if (tid == 0) {
+            for (int s = 0; s < 8; ++s)
+                umma::mma_tf32(tmem + 64u, umma::kmajor_desc_lbo<LBO>(a2_addr + 2u * LBO * s, 64), umma::kmajor_desc(b2_addr + 256u * s, 64), idesc_u, s > 0);
+            umma::commit(&bar_u);
+        }
+
+        // ---- (4) dW0T[col][h] += sum_p X1[p][col] dz[p][h]   (mma.sync; A = X1^T, B = dz read from the K-major tiles); hidden tile = warp
+        {
+            // fragment addresses in the core-matrix layout: point 8 ks + t (+4) -> ks * (K/4) * LBO + t * 16 (+64); column c -> (c / 4) * LBO + (c % 4) * 4.
+            // The MMA's row slots (g, g + 8) of an m-tile carry the ADJACENT columns (2g, 2g + 1) of X1 (any bijection works as long as
+            // the flush below undoes it), so a0 / a1 and a2 / a3 come out of one 64-bit load each.
+            const uint8_t *ab = a1 + (g >> 1) * LBO + (g & 1) * 8 + t * 16;               // columns 2g, 2g + 1 of m-tile 0; m-tile mt: + mt * 4 * LBO
+            const uint8_t *bb0 = a2 + (2 * warp + (g >> 2)) * LBO + (g & 3) * 4 + t * 16;   // hidden 8 warp + g
+#pragma unroll 2
+            for (int ks = 0; ks < 16; ++ks) {
+                const uint8_t *ak = ab + ks * (kK1 / 4) * LBO, *bk = bb0 + ks * (64 / 4) * LBO;
+                const uint32_t b00 = *reinterpret_cast<const uint32_t *>(bk), b01 = *reinterpret_cast<const uint32_t *>(bk + 64);
+#pragma unroll
+                for (int mt = 0; mt < kNMT; ++mt) {
+                    if (16 * mt + 16 <= KF && 16 * mt >= 2 * (int)n_active) continue;   // feature-only tile beyond the active levels
+                    const bool in_tile = 16 * mt + 2 * g < kK1;      // the last m-tile holds kK1 - 32 = 8 columns: row slots g >= 4 are empty
+                    uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+                    if (in_tile) {
+                        lo = *reinterpret_cast<const uint2 *>(ak + mt * 4 * LBO);          // point k-slot t:     columns 2g, 2g + 1
+                        hi = *reinterpret_cast<const uint2 *>(ak + mt * 4 * LBO + 64);     // point k-slot t + 4
+                    }
+                    const uint32_t a[4] = {lo.x, lo.y, hi.x, hi.y};
+                    mma_tf32(wacc[mt], a, b00, b01);
+                }
+            }
+        }
+
+        // ---- hand d loss / d features (this half's 8 level slots) and the point to the scatter kernel
+        if (!umma::mbar_wait(&bar_u, phase)) failed = true;
+        umma::fence_after_sync();
+        {
+            const int64_t q = q0 + tj;
+            if (half == 0 && valid) ws_pos[(int64_t)tk * qcap + q] = make_float4(px, py, pz, dsdf != 0.f ? 1.f : 0.f);
+            if (8 * half < (int)n_active) {                           // warp-uniform
+                float u[16];
+                umma::tmem_ld16(tmem_lane + 64u + 16u * (uint32_t)half, u);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int l2 = 0; l2 < 8; ++l2) {
+                    const int l = 8 * half + l2;
+                    if (valid && l < (int)n_active) ws_dfeat[((int64_t)l * SNB_PATCH + tk) * qcap + q] = make_float2(u[2 * l2], u[2 * l2 + 1]);
+                }
+            }
+        }
+        phase ^= 1u;
+        umma::fence_before_sync();
+        __syncthreads();          // tiles a1 / a2 and both accumulators are free again
+        umma::fence_after_sync();
+    }
+
+    // ---- flush
+#pragma unroll
+    for (int mt = 0; mt < kNMT; ++mt) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = 16 * mt + 2 * g + (c >> 1), h = 8 * warp + 2 * t + (c & 1);   // row slots (g, g + 8) = columns (2g, 2g + 1)
+            float *dst = nullptr;
+            if (col < KF) { if (col < 2 * (int)n_active) dst = net_grad + kOffW0T + (3 + col) * kH + h; }
+            else if (col < kColXlo) dst = net_grad + kOffW0T + (col - kColXhi) * kH + h;
+            else if (col < kColOne) dst = net_grad + kOffW0T + (col - kColXlo) * kH + h;
+            else if (col == kColOne) dst = net_grad + kOffB0 + h;
+            if (dst && wacc[mt][c] != 0.f) atomicAdd(dst, wacc[mt][c]);
+        }
+    }
+    warp_transpose_reduce32(accH, lane);
+    atomicAdd(net_grad + kOffW1 + 32 * half + lane, accH[0]);
+    if (half == 0 && lane == 0) atomicAdd(net_grad + kOffB1, accB1);
+    if (failed && tid == 0 && err_flag) atomicExch(err_flag, 1);
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kBwdTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// hash-table scatter of the split backward
+// ---------------------------------------------------------------------------------------------
+// table_grad[level][corner entry] += trilinear weight * d loss / d feature, for every (point, level, corner).  What bounds it is the
+// L2 reduction path: ~97 reduction SECTORS (32 B) per clock chip-wide = 190 G/s at 1.965 GHz, independent of the operand width and of
+// how many lanes of one instruction fall into the sector (scripts/micro/red_rate.cu, profiles/r02_red_rate_microbench.txt).  So:
+//   * a warp takes 32 consecutive samples q of ONE in-patch ray (neighbours along the ray share grid cells on all but the finest
+//     levels) and loops over the levels;
+//   * writer role: lane = point; it computes the cell and its 8 weighted contributions (float2 each) and parks them with the cell
+//     coordinates in shared memory;
+//   * reader role: lane = (quarter of the warp, corner c); it walks the 8 points of its quarter, sums corner c's contribution while
+//     the cell stays the same and issues ONE red.global.add.v2.f32 per run.  Coarse levels collapse to one reduction per corner and
+//     quarter; on fine levels every point flushes, but one instruction then carries the 8 corners of 4 points in adjacent lanes and
+//     x-neighbour corners (entry h and h ^ 1 / h ^ 3 for a hashed level, idx and idx + 1 for a dense one) share a 32-byte sector
+//     in 3 of 4 cases -> 5 instead of 8 sector requests per point and level.
+// Shared memory is double-buffered over the levels, so one __syncwarp per level suffices.
+constexpr int kScatWarps = 8;
+constexpr int kScatRow = 9;     // float2 per point row (8 corners + 1 pad): 18-word stride, conflict-free 64-bit accesses
+
+__global__ void __launch_bounds__(32 * kScatWarps, 4) hash_scatter_kernel(LevelTable lt, uint32_t n_active, const int *__restrict__ totals, int64_t qcap,
+                                                                          const float4 *__restrict__ ws_pos, const float2 *__restrict__ ws_dfeat,
+                                                                          float *__restrict__ table_grad) {
+    __shared__ __align__(16) float2 s_val[kScatWarps][2][32 * kScatRow];
+    __shared__ __align__(16) uint4 s_cell[kScatWarps][2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qd8 = lane & ~7, cn = lane & 7;
+    const int64_t Q = (int64_t)totals[0] + totals[1];
+    const int64_t n_chunks = (Q + 31) >> 5, n_tasks = n_chunks * SNB_PATCH;
+    for (int64_t task = (int64_t)blockIdx.x * kScatWarps + warp; task < n_tasks; task += (int64_t)gridDim.x * kScatWarps) {
+        const int k = (int)(task % SNB_PATCH);
+        const int64_t q = (task / SNB_PATCH) * 32 + lane;
+        float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < Q) pw = __ldg(ws_pos + (int64_t)k * qcap + q);
+        const bool live = pw.w != 0.f;
+        const float2 *gp = ws_dfeat + (int64_t)k * qcap + q;
+        float2 g_next = make_float2(0.f, 0.f);
+        if (live && n_active > 0) g_next = __ldg(gp);
+        for (uint32_t l = 0; l < n_active; ++l) {
+            const float2 g = g_next;
+            if (live && l + 1 < n_active) g_next = __ldg(gp + (int64_t)(l + 1) * SNB_PATCH * qcap);
+            const LevelCtx c = lt.lv[l];
+            const int buf = (int)(l & 1u);
+            // ---- writer: this lane's point.  Run structure of the warp as ONE bit mask: bit p set <=> point p starts a run (its cell
+            // differs from its left neighbour's, or it opens a quarter).  Dead lanes (g = 0) contribute zeros and may sit inside any run.
+            const Cell cell = cell_of(c, pw.x, pw.y, pw.z);
+            const uint32_t px = __shfl_up_sync(0xffffffffu, cell.g[0], 1), py = __shfl_up_sync(0xffffffffu, cell.g[1], 1),
+                           pz = __shfl_up_sync(0xffffffffu, cell.g[2], 1);
+            const bool head = (lane & 7) == 0 || cell.g[0] != px || cell.g[1] != py || cell.g[2] != pz;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            s_cell[warp][buf][lane] = make_uint4(cell.g[0], cell.g[1], cell.g[2], 0u);
+            float2 *row = &s_val[warp][buf][lane * kScatRow];
+#pragma unroll
+            for (uint32_t cc = 0; cc < 8; ++cc) {
+                const float w = corner_weight(cell, cc);
+                row[cc] = make_float2(w * g.x, w * g.y);
+            }
+            __syncwarp();
+            // ---- reader: corner cn of the 8 points of this quarter; one reduction per run, issued at the run's LAST point (bit p + 1
+            // of `heads` set, or end of the quarter) with that point's own cell -- every point of a run has the same one
+            float2 *gt = reinterpret_cast<float2 *>(table_grad) + c.offset;
+            const uint4 *cq = &s_cell[warp][buf][qd8];
+            const float2 *vq = &s_val[warp][buf][qd8 * kScatRow + cn];
+            const uint32_t tails = ((heads >> qd8) >> 1) | 0x80u;      // bit i: point i closes a run
+            const uint32_t bx = cn & 1u, by = (cn >> 1) & 1u, bz = (uint32_t)cn >> 2;
+            float ax = 0.f, ay = 0.f;
+            if (c.hashed) {     // level-uniform: idx = x ^ y * 2654435761 ^ z * 805459861 mod size (size a power of two for every hashed level)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 v = vq[i * kScatRow];
+                    ax += v.x; ay += v.y;
+                    if ((tails >> i) & 1u) {
+                        if (ax != 0.f || ay != 0.f) {
+                            const uint4 cg = cq[i];
+                            const uint32_t idx = (cg.x + bx) ^ ((cg.y + by) * 2654435761u) ^ ((cg.z + bz) * 805459861u);
+                            atomicAdd(gt + level_mod(c, idx), make_float2(ax, ay));
+                        }
+                        ax = 0.f; ay = 0.f;
+                    }
+                }
+            } else {            // dense level: the generic index (stride loop of tiny-cuda-nn's grid_index)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 v = vq[i * kScatRow];
+                    ax += v.x; ay += v.y;
+                    if ((tails >> i) & 1u) {
+                        if (ax != 0.f || ay != 0.f) {
+                            const uint4 cg = cq[i];
+                            Cell kc;
+                            kc.g[0] = cg.x; kc.g[1] = cg.y; kc.g[2] = cg.z;
+                            atomicAdd(gt + corner_index(c, kc, (uint32_t)cn), make_float2(ax, ay));
+                        }
+                        ax = 0.f; ay = 0.f;
+                    }
+                }
+            }
+        }
+        __syncwarp();   // the next task's first level reuses buffer 0 (or 1): every lane must be done reading
+    }
+}
+
 static int32_t check_net(const snb_net *net, const char *who) {
     SNB_REQUIRE(net, SNB_ERR_NULL, "%s: null net", who);
     SNB_REQUIRE(net->table_f16 && net->net, SNB_ERR_NULL, "%s: null table/net", who);
@@ -709,35 +1111,71 @@ extern "C" int32_t snb_sdf_fwd_patch(const snb_patch_batch *b, const snb_net *ne
     return SNB_OK;
 }
 
-extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const void *feats,
-                                     const float *d_sdf0, const float *d_sdf1, float *table_grad, float *net_grad,
-                                     snb_stream_t stream) {
+// workspace of the split backward: [ ws_pos float4[9 * qcap] | ws_dfeat float2[n_levels * 9 * qcap] ],  qcap = capacity + end_capacity
+extern "C" int64_t snb_sdf_bwd_workspace_bytes(int32_t n_levels, int64_t capacity, int64_t end_capacity) {
+    if (n_levels < 1 || n_levels > SNB_MAX_LEVELS || capacity < 0 || end_capacity < 0) return -1;
+    const int64_t qcap = capacity + end_capacity;
+    return (int64_t)SNB_PATCH * qcap * (int64_t)(sizeof(float4) + (size_t)n_levels * sizeof(float2));
+}
+
+extern "C" int32_t snb_sdf_bwd_patch_ws(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const void *feats,
+                                        const float *d_sdf0, const float *d_sdf1, float *table_grad, float *net_grad, void *workspace,
+                                        int64_t workspace_bytes, snb_stream_t stream) {
     int32_t rc = check_net(net, "sdf_bwd_patch");
     if (rc) return rc;
     rc = check_patch_args(b, sm, "sdf_bwd_patch");
     if (rc) return rc;
     SNB_REQUIRE(feats && d_sdf0 && d_sdf1 && table_grad && net_grad, SNB_ERR_NULL, "sdf_bwd_patch: null buffer");
     SNB_REQUIRE(aligned(table_grad, 8), SNB_ERR_ALIGN, "sdf_bwd_patch: table_grad must be 8-byte aligned");
+    SNB_REQUIRE(!workspace || aligned(workspace, 16), SNB_ERR_ALIGN, "sdf_bwd_patch: workspace must be 16-byte aligned");
     static const size_t smem = sizeof(float) * (kNetFloats + kTile * kDzStride + kTile * kXStride);
     // tcgen05 kernel (KF = 8 tiles up to 4 active levels, KF = 32 beyond): 140 vs 178 us at 1 level, 75 vs 113 us at 4, 370 vs 532 us
-    // at 14 against the FMA kernel, which SNB_BWD_UMMA=0 still selects for cross-checks (tests/test_gpu_fused.py).
+    // at 14 against the FMA kernel, which SNB_BWD_UMMA=0 still selects for cross-checks (tests/test_gpu_fused.py).  Beyond 4 levels the
+    // scatter moves into its own high-occupancy kernel when the caller provides the workspace (SNB_BWD_SPLIT=0: keep it fused).
     static const int use_umma = getenv("SNB_BWD_UMMA") ? atoi(getenv("SNB_BWD_UMMA")) : 1;
+    static const int use_split = getenv("SNB_BWD_SPLIT") ? atoi(getenv("SNB_BWD_SPLIT")) : 1;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(sdf_bwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(sdf_bwd_patch_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg<32>::kSmem);
+        cudaFuncSetAttribute(sdf_bwd_mlp_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_bytes<128>());
+        cudaFuncSetAttribute(sdf_bwd_mlp_umma_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_bytes<192>());
         cudaFuncSetAttribute(sdf_bwd_patch_umma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdCfg<8>::kSmem);
         configured = true;
     }
     const LevelTable ltab = make_level_table(net->meta);
+    const int64_t qcap = sm->capacity + sm->end_capacity;
+    const bool split = use_umma && use_split && net->n_active > 4 && workspace &&
+                       workspace_bytes >= snb_sdf_bwd_workspace_bytes((int32_t)net->meta.n_levels, sm->capacity, sm->end_capacity);
+    if (split) {
+        float4 *ws_pos = reinterpret_cast<float4 *>(workspace);
+        float2 *ws_dfeat = reinterpret_cast<float2 *>(ws_pos + (int64_t)SNB_PATCH * qcap);
+        static const int lbo = getenv("SNB_BWD_LBO") ? atoi(getenv("SNB_BWD_LBO")) : 192;
+        if (lbo == 128)
+            sdf_bwd_mlp_umma_kernel<128><<<kNumSMs * 2, kMlpThreads, mlp_smem_bytes<128>(), S(stream)>>>(
+                *b, *net, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, net_grad, sm->totals + 2, ws_dfeat, ws_pos, qcap);
+        else
+            sdf_bwd_mlp_umma_kernel<192><<<kNumSMs * 2, kMlpThreads, mlp_smem_bytes<192>(), S(stream)>>>(
+                *b, *net, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, net_grad, sm->totals + 2, ws_dfeat, ws_pos, qcap);
+        SNB_LAUNCH_CHECK("sdf_bwd_patch (mlp)");
+        hash_scatter_kernel<<<kNumSMs * 4, 32 * kScatWarps, 0, S(stream)>>>(ltab, net->n_active, sm->totals, qcap, ws_pos, ws_dfeat, table_grad);
+        SNB_LAUNCH_CHECK("sdf_bwd_patch (scatter)");
+        return SNB_OK;
+    }
     if (use_umma && net->n_active <= 4)
-        sdf_bwd_patch_umma_kernel<8><<<kNumSMs * BwdCfg<8>::kMinBlocks, 128, BwdCfg<8>::kSmem, S(stream)>>>(*b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1,
-                                                                                                            table_grad, net_grad, sm->totals + 2);
+        sdf_bwd_patch_umma_kernel<8><<<kNumSMs * BwdCfg<8>::kMinBlocks, 128, BwdCfg<8>::kSmem, S(stream)>>>(
+            *b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad, sm->totals + 2);
     else if (use_umma)
-        sdf_bwd_patch_umma_kernel<32><<<kNumSMs * BwdCfg<32>::kMinBlocks, 128, BwdCfg<32>::kSmem, S(stream)>>>(*b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1,
-                                                                                                               table_grad, net_grad, sm->totals + 2);
+        sdf_bwd_patch_umma_kernel<32><<<kNumSMs * BwdCfg<32>::kMinBlocks, 128, BwdCfg<32>::kSmem, S(stream)>>>(
+            *b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad, sm->totals + 2);
     else
         sdf_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, ltab, *sm, (const __half2 *)feats, d_sdf0, d_sdf1, table_grad, net_grad);
     SNB_LAUNCH_CHECK("sdf_bwd_patch");
     return SNB_OK;
+}
+
+extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const void *feats,
+                                     const float *d_sdf0, const float *d_sdf1, float *table_grad, float *net_grad,
+                                     snb_stream_t stream) {
+    return snb_sdf_bwd_patch_ws(b, net, sm, feats, d_sdf0, d_sdf1, table_grad, net_grad, nullptr, 0, stream);
 }

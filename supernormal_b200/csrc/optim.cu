@@ -562,7 +562,7 @@ extern "C" int32_t snb_train_tail(const snb_train_ctx *c, float lr, int32_t step
     if (ds_next && n_patches_next > 0) {
         SNB_REQUIRE(out_next, SNB_ERR_NULL, "train_tail: null sampler output");
         SNB_REQUIRE(ds_next->W > 3 && ds_next->H > 3 && ds_next->n_train > 0 && ds_next->n_images > 0, SNB_ERR_ARG, "train_tail: bad dataset sizes");
-        SNB_REQUIRE(ds_next->normals && ds_next->masks && ds_next->intrinsics_inv && ds_next->pose && ds_next->v_inverse && ds_next->train_ids,
+        SNB_REQUIRE(ds_next->normals && ds_next->masks && ds_next->intrinsics_inv && ds_next->pose && ds_next->train_ids,
                     SNB_ERR_NULL, "train_tail: null dataset tensor");
         SNB_REQUIRE(out_next->rays_o && out_next->rays_d && out_next->plane_n && out_next->near_ && out_next->far_ && out_next->v_inv &&
                         out_next->normal_gt && out_next->mask, SNB_ERR_NULL, "train_tail: null sampler output tensor");
@@ -616,7 +616,7 @@ extern "C" int32_t snb_train_tail_peer(const snb_train_ctx *c, const snb_peer_gr
     if (ds_next && n_patches_next > 0) {
         SNB_REQUIRE(out_next, SNB_ERR_NULL, "train_tail_peer: null sampler output");
         SNB_REQUIRE(ds_next->W > 3 && ds_next->H > 3 && ds_next->n_train > 0 && ds_next->n_images > 0, SNB_ERR_ARG, "train_tail_peer: bad dataset sizes");
-        SNB_REQUIRE(ds_next->normals && ds_next->masks && ds_next->intrinsics_inv && ds_next->pose && ds_next->v_inverse && ds_next->train_ids,
+        SNB_REQUIRE(ds_next->normals && ds_next->masks && ds_next->intrinsics_inv && ds_next->pose && ds_next->train_ids,
                     SNB_ERR_NULL, "train_tail_peer: null dataset tensor");
         SNB_REQUIRE(out_next->rays_o && out_next->rays_d && out_next->plane_n && out_next->near_ && out_next->far_ && out_next->v_inv &&
                         out_next->normal_gt && out_next->mask, SNB_ERR_NULL, "train_tail_peer: null sampler output tensor");

@@ -87,7 +87,7 @@ extern "C" int32_t snb_sample_patches(const snb_dataset *ds, int32_t n_patches, 
     SNB_REQUIRE(ds && out, SNB_ERR_NULL, "sample_patches: null struct");
     SNB_REQUIRE(n_patches >= 0 && ds->W > 3 && ds->H > 3 && ds->n_train > 0 && ds->n_images > 0, SNB_ERR_ARG, "sample_patches: bad sizes");
     if (n_patches == 0) return SNB_OK;
-    SNB_REQUIRE(ds->normals && ds->masks && ds->intrinsics_inv && ds->pose && ds->v_inverse && ds->train_ids, SNB_ERR_NULL, "sample_patches: null dataset tensor");
+    SNB_REQUIRE(ds->normals && ds->masks && ds->intrinsics_inv && ds->pose && ds->train_ids, SNB_ERR_NULL, "sample_patches: null dataset tensor");
     SNB_REQUIRE(out->rays_o && out->rays_d && out->plane_n && out->near_ && out->far_ && out->v_inv && out->normal_gt && out->mask, SNB_ERR_NULL,
                 "sample_patches: null output");
     sample_patches_kernel<<<(unsigned)cdiv((int64_t)n_patches * SNB_PATCH, 256), 256, 0, S(stream)>>>(*ds, n_patches, seed, step, *out);
@@ -132,7 +132,8 @@ extern "C" int32_t snb_train_fwd_bwd(const snb_train_ctx *c, float step_size, fl
     if ((rc = snb_render_fused(&c->batch, &c->net, &c->samples, c->sdf, normal_weight, mask_weight, eikonal_weight, c->comp, c->wsum, c->d_sdf0,
                                c->d_sdf1, c->stats, stream))) return rc;
     cudaMemsetAsync(c->net_grad, 0, sizeof(float) * SNB_NET_FLOATS, S(stream));
-    if ((rc = snb_sdf_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad, stream)))
+    if ((rc = snb_sdf_bwd_patch_ws(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad,
+                                   c->bwd_workspace, c->bwd_workspace_bytes, stream)))
         return rc;
     return snb_unfold_grads(c->n_levels, c->flat_param, c->net_grad, c->stats, c->flat_grad, stream);
 }
@@ -152,7 +153,8 @@ extern "C" int32_t snb_train_fwd_bwd_lean(const snb_train_ctx *c, float step_siz
     if ((rc = snb_sdf_fwd_patch(&c->batch, &c->net, &c->samples, c->sdf, c->feats, stream))) return rc;
     if ((rc = snb_render_fused(&c->batch, &c->net, &c->samples, c->sdf, normal_weight, mask_weight, eikonal_weight, c->comp, c->wsum, c->d_sdf0,
                                c->d_sdf1, c->stats, stream))) return rc;
-    return snb_sdf_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad, stream);
+    return snb_sdf_bwd_patch_ws(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad,
+                                c->bwd_workspace, c->bwd_workspace_bytes, stream);
 }
 
 extern "C" int32_t snb_train_optim(const snb_train_ctx *c, float lr, int32_t step_count, float grad_scale, snb_stream_t stream) {

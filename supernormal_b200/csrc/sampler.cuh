@@ -46,8 +46,23 @@ __device__ __forceinline__ void sample_patch_ray(const snb_dataset &ds, int n_pa
 #pragma unroll
     for (int a = 0; a < 3; ++a) out.normal_gt[3 * rk + a] = __ldg(ds.normals + 3 * pix + a);
     out.mask[rk] = __ldg(ds.masks + pix);
+    if (ds.v_inverse) {   // precomputed table (Dataset.V_inverse_all, models/dataset_loader.py:114-137): 36 B per pixel, 226 MB for DiLiGenT-MV
 #pragma unroll
-    for (int a = 0; a < 9; ++a) out.v_inv[9 * rk + a] = __ldg(ds.v_inverse + 9 * pix + a);
+        for (int a = 0; a < 9; ++a) out.v_inv[9 * rk + a] = __ldg(ds.v_inverse + 9 * pix + a);
+    } else {
+        // closed form of the same inverse.  V = [v; r; d] (rows) with v = R p (the unit ray direction), r = R e_x, d = R e_y, i.e.
+        // V = A R^T with A = [p; e_x; e_y] in the camera frame, so V^-1 = R A^-1 (R orthonormal: load_K_Rt_from_P transposes the rotation
+        // of cv2.decomposeProjectionMatrix) and A^-1 = [[0, 1, 0], [0, 0, 1], [1/pz, -px/pz, -py/pz]]:
+        //   V^-1[:, 0] = R[:, 2] / pz,   V^-1[:, 1] = R[:, 0] - R[:, 2] px / pz,   V^-1[:, 2] = R[:, 1] - R[:, 2] py / pz
+        const float ipz = 1.f / p[2], qx = p[0] * ipz, qy = p[1] * ipz;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float r0 = __ldg(Pm + 4 * a), r1 = __ldg(Pm + 4 * a + 1), r2 = __ldg(Pm + 4 * a + 2);
+            out.v_inv[9 * rk + 3 * a] = r2 * ipz;
+            out.v_inv[9 * rk + 3 * a + 1] = fmaf(-r2, qx, r0);
+            out.v_inv[9 * rk + 3 * a + 2] = fmaf(-r2, qy, r1);
+        }
+    }
     if (k == SNB_PATCH / 2) {
         out.rays_o[3 * i] = o[0]; out.rays_o[3 * i + 1] = o[1]; out.rays_o[3 * i + 2] = o[2];
         out.plane_n[3 * i] = __ldg(Pm + 2); out.plane_n[3 * i + 1] = __ldg(Pm + 6); out.plane_n[3 * i + 2] = __ldg(Pm + 10);

@@ -53,19 +53,47 @@ __device__ __forceinline__ float log1p_poly01(float u) {
     return fmaf(p, u, 2.2159764512252877e-07f);
 }
 
+// MUFU ops as their .ftz PTX forms (see softplus100_both_lg2 below for why)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <bool SAT = true>
 __device__ __forceinline__ float softplus100(float z) {
-    float bz = 100.f * z;
-    if (SAT && !__any_sync(__activemask(), fabsf(bz) < kSoftplusSat)) return fmaxf(z, 0.f);
-    return fmaf(0.01f, log1p_poly01(__expf(-fabsf(bz))), fmaxf(z, 0.f));
+    if (SAT && !__any_sync(__activemask(), fabsf(z) < 0.01f * kSoftplusSat)) return fmaxf(z, 0.f);
+    return fmaf(0.01f, log1p_poly01(ex2_ftz(fabsf(z) * -144.26950408889634f)), fmaxf(z, 0.f));
 }
 // softplus and its derivative sigmoid(100 z): one EX2 and one RCP
 __device__ __forceinline__ void softplus100_both(float z, float &sp, float &sg) {
-    const float bz = 100.f * z;
-    const float u = __expf(-fabsf(bz));
+    const float u = ex2_ftz(fabsf(z) * -144.26950408889634f);     // the same u as softplus100: the two forms agree bit for bit on sp
     sp = fmaf(0.01f, log1p_poly01(u), fmaxf(z, 0.f));
-    const float r = __fdividef(1.f, 1.f + u);
-    sg = bz >= 0.f ? r : u * r;
+    const float r = rcp_ftz(1.f + u);
+    sg = z >= 0.f ? r : u * r;
+}
+
+// the same pair with the logarithm on the XU pipe: log1p(u) = -ln(r), r = 1 / (1 + u) = sigmoid(|100 z|) in [0.5, 1], so
+// softplus = max(z, 0) - (ln 2 / 100) lg2(r): EX2 + RCP + LG2 and 7 FMAs fewer than the polynomial.  For kernels whose issue slots, not
+// the XU pipe, are the scarce resource (the 256-thread MLP backward: 19 % XU utilisation).  MUFU.LG2's absolute error near r = 1 is
+// 2^-22, i.e. 1.6e-9 on softplus -- the class of the polynomial form.  The three MUFU ops are issued as their .ftz PTX forms: the
+// non-ftz intrinsics (__expf, __log2f, __fdividef) wrap every MUFU in a denormal rescue (FSETP + FMUL by 2^24 + FSEL + FADD -24, plus
+// predicate spills through LOP3) that tripled the per-value instruction count (profiles/r02_ncu_bwd_split_v4_it4800.txt); here u
+// underflowing to 0 is exact (|100 z| > 87: softplus = max(z, 0), derivative 0 / 1) and r is never denormal.
+__device__ __forceinline__ void softplus100_both_lg2(float z, float &sp, float &sg) {
+    const float u = ex2_ftz(fabsf(z) * -144.26950408889634f);     // exp(-|100 z|)
+    const float r = rcp_ftz(1.f + u);
+    sp = fmaf(-0.0069314718056f, lg2_ftz(r), fmaxf(z, 0.f));
+    sg = z >= 0.f ? r : u * r;                                     // sigmoid(100 z)
 }
 
 __device__ __forceinline__ void rank1_update(float (&acc)[kH], const float *__restrict__ w_row, float v) {

@@ -33,6 +33,26 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t smem_byte_addr, int K) 
     return d;
 }
 
+// The same layout with a padded leading-dimension byte offset LBO (> 128, multiple of 16): core (r/8, k/4) at (r/8) * (K/4) * LBO +
+// (k/4) * LBO.  tcgen05 only sees a different stride in the descriptor; the threads gain conflict-free TRANSPOSED reads of the tile:
+// the mma.sync fragments of the weight-gradient contraction read 4-byte words at (k/4 varies with lane bit 2) -- with LBO = 128 lanes
+// g and g + 4 of a fragment load hit the same bank (2 wavefronts per LDS, 8.7 M conflicts per launch in
+// profiles/r02_ncu_bwd_split_v2_it4800.txt); with LBO = 192 (48 words = 16 mod 32) the 32 lanes cover the 32 banks.
+template <int LBO>
+__host__ __device__ constexpr uint32_t tile_bytes_lbo(int rows, int K) { return (uint32_t)(rows / 8) * (uint32_t)(K / 4) * (uint32_t)LBO; }
+template <int LBO>
+__device__ __forceinline__ uint32_t kmajor_off_lbo(int r, int k, int K) {
+    return (uint32_t)(((r >> 3) * (K >> 2) + (k >> 2)) * LBO + (r & 7) * 16 + (k & 3) * 4);
+}
+template <int LBO>
+__device__ __forceinline__ uint64_t kmajor_desc_lbo(uint32_t smem_byte_addr, int K) {
+    uint64_t d = (uint64_t)((smem_byte_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((uint32_t)LBO >> 4) << 16;
+    d |= (uint64_t)((((uint32_t)(K >> 2) * (uint32_t)LBO) >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
 // MN-major TF32 operands are NOT available in this layout: tcgen05 accepts them only with the 128B_BASE32B swizzle (measured:
 // wrong results with a no-swizzle MN-major descriptor), and for M = 128 the N extent must be a multiple of 16.  Contractions over
 // the row index of these tiles therefore go through warp-level mma.sync (fused_sdf.cu, step (4) of the backward).

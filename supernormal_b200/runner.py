@@ -40,6 +40,49 @@ def render_patches(tr: FusedTrainer, batch: dict, step_size: float, jitter: Opti
 
 
 @torch.no_grad()
+def render_normal_pixel_based(tr: FusedTrainer, rays_o: torch.Tensor, rays_d: torch.Tensor, near: torch.Tensor, far: torch.Tensor,
+                              step_size: Optional[float] = None, stratified: bool = True) -> Dict[str, torch.Tensor]:
+    """NeuSRenderer.render_normal_pixel_based (models/renderer.py:278-351): per-pixel validation render.  Per-ray marching through the
+    occupancy grid with the NeuS alpha of the centre-ray form as alpha_fn (alpha_thre = 0, early_stop_eps = 1e-3), alpha again on the
+    surviving samples, analytic normals SDFNetwork.gradient at the interval midpoints (snb_sdf_eval_grad: SDF + gradient in one
+    pass, no autograd graph), render_weight_from_alpha and accumulate_along_rays (the P = 1 kernels of rows a10 / a11).
+    -> comp_normal [n,3], comp_depth [n,1] (the reference's return values) + weight_sum [n,1], n_samples."""
+    from . import nerfacc_api as na
+    m = tr.model
+    m.prep()
+    inv_s = m.net[2369]                       # clip(exp(10 variance), 1e-6, 1e6), folded by snb_prep_net (sdf_core.cuh:kOffInvS)
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+
+    def alpha_fn(t_starts, t_ends, ray_indices):
+        ridx = ray_indices.long()
+        o, d = rays_o[ridx], rays_d[ridx]
+        ps, pe = o + d * t_starts, o + d * t_ends
+        nxt = torch.cat([t_starts[1:], t_starts[-1:]], 0)
+        diff = ((t_ends - nxt) != 0).squeeze(-1)                    # models/renderer.py:288-293
+        sdf_all = m.sdf(torch.cat([ps, pe[diff].reshape(-1, 3)], 0))
+        s0 = sdf_all[: ps.shape[0]]
+        s1 = torch.cat([s0[1:], s0[-1:]], 0)
+        s1[diff] = sdf_all[ps.shape[0]:]
+        c, n = torch.sigmoid(s0 * inv_s), torch.sigmoid(s1 * inv_s)
+        return ((c - n + 1e-5) / (c + 1e-5)).view(-1).clip(0.0, 1.0).reshape(-1, 1)
+
+    step = tr.step_size(tr.iter_step) if step_size is None else step_size
+    ridx, t0, t1 = na.ray_marching(rays_o, rays_d, t_min=near.reshape(-1), t_max=far.reshape(-1), grid=tr.grid, render_step_size=step,
+                                   stratified=stratified, cone_angle=0.0, alpha_thre=0.0, early_stop_eps=1e-3, alpha_fn=alpha_fn)
+    n = rays_o.shape[0]
+    if ridx.numel() == 0:
+        z = torch.zeros(n, 1, device=rays_o.device)
+        return {"comp_normal": torch.zeros(n, 3, device=rays_o.device), "comp_depth": z, "weight_sum": z.clone(), "n_samples": 0}
+    alpha = alpha_fn(t0, t1, ridx)
+    mid = (t0 + t1) / 2.0
+    _, grad = m.sdf_and_gradient(rays_o[ridx.long()] + rays_d[ridx.long()] * mid)
+    w = na.render_weight_from_alpha(alpha, ray_indices=ridx, n_rays=n)
+    return {"comp_normal": na.accumulate_along_rays(w, ridx, values=grad, n_rays=n),
+            "comp_depth": na.accumulate_along_rays(w, ridx, values=mid, n_rays=n),
+            "weight_sum": na.accumulate_along_rays(w, ridx, values=None, n_rays=n), "n_samples": int(ridx.numel())}
+
+
+@torch.no_grad()
 def validate_normal_patch_based(tr: FusedTrainer, idx: int, eval_patch_size: int = 1024, stratified: bool = True) -> torch.Tensor:
     """World-space rendered normal map [3*(H//3), 3*(W//3), 3] of view idx from non-overlapping 3x3 patches
     (Dataset.gen_patches_at, models/dataset_loader.py:177-221; tiling loop of exp_runner.py:423-453)."""

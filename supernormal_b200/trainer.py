@@ -59,7 +59,7 @@ class SnbTrainCtx(C.Structure):
                 ("net_grad", C.c_void_p), ("sdf", C.c_void_p), ("feats", C.c_void_p), ("d_sdf0", C.c_void_p), ("d_sdf1", C.c_void_p),
                 ("comp", C.c_void_p), ("wsum", C.c_void_p), ("dcomp", C.c_void_p), ("dwsum", C.c_void_p), ("stats", C.c_void_p),
                 ("jitter", C.c_void_p), ("roi", C.c_void_p), ("grid_binary", C.c_void_p), ("res_x", C.c_int32), ("res_y", C.c_int32),
-                ("res_z", C.c_int32)]
+                ("res_z", C.c_int32), ("bwd_workspace", C.c_void_p), ("bwd_workspace_bytes", C.c_int64)]
 
 
 class SnbPeerGroup(C.Structure):
@@ -260,6 +260,9 @@ class SampleBuffers:
         self.dcomp = torch.zeros(n_patches, P, 3, **f32)
         self.dwsum = torch.zeros(n_patches, P, **f32)
         self.stats = torch.zeros(8, **f32)
+        # workspace of the split backward (snb_sdf_bwd_patch_ws): positions + d loss / d features of every point, [level][ray][sample]
+        self.bwd_ws_bytes = int(_lib.lib().snb_sdf_bwd_workspace_bytes(n_levels, self.capacity, self.end_capacity))
+        self.bwd_ws = torch.empty(self.bwd_ws_bytes, dtype=torch.uint8, device=device)
         self.struct = SnbSamples(self.capacity, self.end_capacity, scratch_stride, *[t.data_ptr() for t in (
             self.counts, self.end_counts, self.packed_info, self.end_packed, self.totals, self.t0, self.t1,
             self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1)])
@@ -382,7 +385,11 @@ class FusedTrainer:
         self.world_size, self.rank = world_size, rank
         self.n_patches = int(conf["batch_size"])
         assert int(conf["patch_size"]) == 3, "3x3 patches (config/diligent.conf:29)"
-        assert conf.get("gradient_method", "dfd") == "dfd", "fused path implements dfd (the shipped default)"
+        # 'dfd' (both shipped confs): the fully fused step.  'ad' (models/renderer.py:225-226, SDFNetwork.gradient with create_graph=True):
+        # marching, visibility and Adam stay fused, the render stage runs through the drop-in autograd operators (forward_backward_ad).
+        self.gradient_method = conf.get("gradient_method", "dfd")
+        if self.gradient_method not in ("dfd", "ad"):
+            raise NotImplementedError(f"gradient_method {self.gradient_method!r}: 'dfd' and 'ad' are implemented ('fd' is a debugging aid of the reference)")
         # the kernels hard-wire what both shipped confs select; anything else must fail here, not train silently on other maths
         if conf.get("loss_type", "l1") != "l2":     # exp_runner.py:61 defaults to 'l1' when the key is absent
             raise NotImplementedError(f"fused trainer implements loss_type 'l2' (config/diligent.conf, own_objects.conf); got {conf.get('loss_type', 'l1')!r}")
@@ -392,7 +399,7 @@ class FusedTrainer:
         # (SNB_DP=peer, default) or NCCL allreduce + replicated Adam (SNB_DP=nccl, also the fallback when symmetric memory is unavailable)
         self.peer_mode = False
         self.model = None
-        if world_size > 1 and os.environ.get("SNB_DP", "peer") == "peer":
+        if world_size > 1 and os.environ.get("SNB_DP", "peer") == "peer" and self.gradient_method == "dfd":
             import torch.distributed as dist
             ok = 1
             try:
@@ -419,7 +426,7 @@ class FusedTrainer:
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
         self.seed = dp.rank_seed(seed, rank)   # every rank draws its own patches (weak scaling)
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
-        self.lean = self.peer_mode or os.environ.get("SNB_LEAN", "1") != "0"   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
+        self.lean = (self.peer_mode or os.environ.get("SNB_LEAN", "1") != "0") and self.gradient_method == "dfd"   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
                                       # (snb_train_tail) unfolds, runs Adam, folds the updated weights and pre-samples the next batch
         self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
         self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
@@ -434,10 +441,15 @@ class FusedTrainer:
         self._presampled = (-1, 0)     # (iteration, slot) filled ahead by the tail kernel
         self.train_ids = torch.tensor(dataset.train_images, dtype=torch.int32, device=dv)
         # the C ABI reads dense fp32 tensors (torch.inverse may hand back column-major batches)
-        self._ds_tensors = [t.to(dv, torch.float32).contiguous() for t in (dataset.normals, dataset.masks, dataset.intrinsics_all_inv,
-                                                                            dataset.pose_all, dataset.V_inverse_all)]
+        # V_inverse (models/dataset_loader.py:114-137) is computed in closed form inside the sampler; SNB_VINV_TABLE=1 reads the dataset's
+        # precomputed [n_images,H,W,3,3] table instead (36 B per pixel: 226 MB for DiLiGenT-MV) -- tests compare the two
+        self.v_inverse_table = os.environ.get("SNB_VINV_TABLE", "0") == "1"
+        self._ds_tensors = [t.to(dv, torch.float32).contiguous() for t in (dataset.normals, dataset.masks, dataset.intrinsics_all_inv, dataset.pose_all)]
+        if self.v_inverse_table:
+            self._ds_tensors.append(dataset.V_inverse_all.to(dv, torch.float32).contiguous())
         self.ds_struct = SnbDataset(dataset.n_images, dataset.H, dataset.W, len(dataset.train_images),
-                                    *[t.data_ptr() for t in self._ds_tensors], self.train_ids.data_ptr())
+                                    *[t.data_ptr() for t in self._ds_tensors[:4]], self._ds_tensors[4].data_ptr() if self.v_inverse_table else None,
+                                    self.train_ids.data_ptr())
         self._out_structs = [SnbBatchOut(*[ob[k].data_ptr() for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")],
                                          jit.data_ptr()) for ob, jit in zip(self._own, self._own_jitter)]
         self.occs_prev = torch.zeros(self.grid.num_cells, device=dv)
@@ -507,7 +519,7 @@ class FusedTrainer:
                            m.exp_avg.data_ptr(), m.exp_avg_sq.data_ptr(), m.net_grad.data_ptr(), b.sdf.data_ptr(), b.feats.data_ptr(),
                            b.d_sdf0.data_ptr(), b.d_sdf1.data_ptr(), b.comp.data_ptr(), b.wsum.data_ptr(), b.dcomp.data_ptr(),
                            b.dwsum.data_ptr(), b.stats.data_ptr(), 0 if jitter is None else jitter.data_ptr(), g.roi_aabb.data_ptr(),
-                           g.binary.data_ptr(), *g._res)
+                           g.binary.data_ptr(), *g._res, b.bwd_ws.data_ptr(), b.bwd_ws_bytes)
 
     def sample_batch(self):
         c = self.conf
@@ -536,6 +548,8 @@ class FusedTrainer:
             ctx = self._ctx(batch, jitter)
             call("snb_train_fwd_bwd_lean" if lean else "snb_train_fwd_bwd", C.byref(ctx), float(step_size), 1e-8, float(c["normal_weight"]),
                  float(c["mask_weight"]), float(c["eikonal_weight"]))
+            if m.n_active > 4 and os.environ.get("SNB_BWD_SPLIT", "1") != "0" and os.environ.get("SNB_BWD_UMMA", "1") != "0":
+                _lib.LAUNCH_COUNT += 1   # beyond 4 live levels the backward is two launches (MLP backward + table scatter)
             return
         bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"],
                                batch["v_inv"], batch["normal_gt"], batch["mask"])
@@ -562,9 +576,108 @@ class FusedTrainer:
                  ptr(b.comp), ptr(b.wsum), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
         if not lean:
             m.net_grad.zero_()
-        call("snb_sdf_bwd_patch", rb, rn, rs, ptr(b.feats), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
+        call("snb_sdf_bwd_patch_ws", rb, rn, rs, ptr(b.feats), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad),
+             ptr(b.bwd_ws), b.bwd_ws_bytes)
         if not lean:
             call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(b.stats), ptr(m.grad))
+
+    def forward_backward_ad(self, batch: dict, step_size: float, jitter: Optional[torch.Tensor]):
+        """One iteration's forward + backward with ANALYTIC normals (gradient_method = 'ad'; models/renderer.py:225-226 and
+        SDFNetwork.gradient, models/fields.py:107-119).  Fused: ray marching + visibility cut + sample compaction (snb_march_visible,
+        snb_compact_samples) and, afterwards, Adam.  Through the drop-in operators under torch autograd: the hash-grid encoding
+        (tcnn_api: first derivative w.r.t. x and the double backward into table and dL/dy, snb_hashgrid_bwd_input /
+        snb_hashgrid_bwd_bwd_input), the fp32 MLP, NeuS alpha (models/renderer.py:164-179), patch weights and accumulation
+        (nerfacc_api) and the losses (exp_runner.py:191-203).  Leaves the gradients w.r.t. (v, g, b, variance | table) in model.grad
+        and the loss terms in buf.stats, like forward_backward(lean=False); one host read-back (the sample counts)."""
+        import torch.nn.functional as F
+        from . import nerfacc_api as na
+        from . import tcnn_api
+        m, b, c = self.model, self.buf, self.conf
+        self.last_batch = batch
+        self._grads_folded = False
+        n = self.n_patches
+        m.prep(batch["mask"], b.stats)      # the marcher's no-grad SDF uses the folded weights
+        m.net_stale = False
+        bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"], batch["v_inv"],
+                               batch["normal_gt"], batch["mask"])
+        net = m.net_struct()
+        rs = C.byref(b.struct)
+        call("snb_march_visible", C.byref(bs), C.byref(net), ptr(self.grid.roi_aabb), *self.grid._res, ptr(self.grid.binary.view(torch.uint8)),
+             float(step_size), ptr(jitter), 1e-8, rs)
+        call("snb_compact_samples", n, rs)
+        S = int(b.totals[0].item())
+        m.grad.zero_()
+        if S == 0:      # models/renderer.py:137-140: nothing to render, the reference skips the iteration
+            b.stats[1:].zero_()
+            return
+        pidx = b.patch_idx[:S].long()
+        t0c, t1c = b.t0[:S, None], b.t1[:S, None]
+        o = batch["rays_o"]                                         # [n,3] (the patch's camera centre)
+        d = batch["rays_d"].view(n, P, 3)
+        pn = batch["plane_n"]
+        # ---- differentiable parameters: leaves over the flat buffer
+        so = m._small_offsets()
+        small = m.small.detach().clone().requires_grad_(True)
+        table = m.table.detach().requires_grad_(True)
+        v0, g0, b0 = small[so["v0"]:so["g0"]].view(H, m.d_in), small[so["g0"]:so["b0"]].view(H, 1), small[so["b0"]:so["v1"]]
+        v1, g1, b1, var = small[so["v1"]:so["g1"]].view(1, H), small[so["g1"]:so["g1"] + 1].view(1, 1), small[so["b1"]:so["b1"] + 1], small[so["var"]]
+        W0, W1 = g0 * v0 / v0.norm(dim=1, keepdim=True), g1 * v1 / v1.norm(dim=1, keepdim=True)     # nn.utils.weight_norm, models/fields.py:66-67
+        if getattr(self, "_ad_enc", None) is None:
+            self._ad_enc = tcnn_api.Encoding(3, dict(c["encoding"])).to(self.device)
+            self._ad_enc.params.requires_grad_(False)
+        enc = self._ad_enc
+        enc.n_active_levels = m.n_active                             # levels >= bindwidth contribute exact zeros (models/fields.py:81-83)
+        # the gathers read the fp16 copy the optimizer kernel maintains (tcnn_api would otherwise recast -- and its cache cannot see the
+        # in-place updates of snb_train_optim)
+        enc._cache_table, enc._cache_key = m.table_f16, (table.data_ptr(), table._version, table.device)
+
+        def sdf_fn(x):                                               # SDFNetwork.forward, models/fields.py:76-99
+            feat = tcnn_api._Encode.apply(enc, x, table).to(torch.float32)
+            h = F.softplus(F.linear(torch.cat([x, feat], 1), W0, b0), beta=100)
+            return F.linear(h, W1, b1)
+
+        with torch.no_grad():                                        # plane fan-out, models/renderer.py:146-159
+            num = (d[:, P // 2] * pn).sum(-1, keepdim=True)[pidx][:, None, :]
+            den = (d * pn[:, None, :]).sum(-1, keepdim=True)[pidx]
+            t0, t1 = t0c[:, None, :] * num / den, t1c[:, None, :] * num / den
+            nxt = torch.cat([t0c[1:], t0c[-1:]], 0)
+            dm = ((t1c - nxt) != 0)[:, 0]
+            p0 = o[pidx][:, None, :] + d[pidx] * t0                  # [S,9,3]
+            p1 = o[pidx][:, None, :] + d[pidx] * t1
+            pos_all = torch.cat([p0, p1[dm]], 0)
+        sdf_all = sdf_fn(pos_all.reshape(-1, 3)).reshape(-1, P, 1)
+        s0 = sdf_all[:S]
+        s1 = torch.cat([s0[1:], s0[-1:]], 0).clone()                 # models/renderer.py:164-169
+        s1[dm] = sdf_all[S:]
+        inv_s = torch.exp(var * 10.0).clip(1e-6, 1e6)
+        cdf0, cdf1 = torch.sigmoid(s0 * inv_s), torch.sigmoid(s1 * inv_s)
+        alpha = ((cdf0 - cdf1 + 1e-5) / (cdf0 + 1e-5)).clip(0.0, 1.0)
+        w = na.render_weight_from_alpha_patch_based(alpha, pidx)
+        with torch.enable_grad():                                    # SDFNetwork.gradient, models/fields.py:107-119
+            x = p0.reshape(-1, 3).detach().requires_grad_(True)
+            y = sdf_fn(x)
+            grads = torch.autograd.grad(y, x, torch.ones_like(y), create_graph=True, retain_graph=True, only_inputs=True)[0].reshape(S, P, 3)
+        wsum = na.accumulate_along_rays_patch_based(w, pidx, n_patches=n)                       # [n,9,1]
+        comp = na.accumulate_along_rays_patch_based(w, pidx, values=grads, n_patches=n)         # [n,9,3]
+        # ---- losses, exp_runner.py:169-203 (l2)
+        mask = (batch["mask"].view(n, P, 1) > 0.5).float()
+        mask_sum = mask.sum() + 1e-5
+        err = (comp - batch["normal_gt"].view(n, P, 3)) * mask
+        normal_loss = (err ** 2).sum() / mask_sum
+        eik = ((torch.linalg.norm(grads, ord=2, dim=-1) - 1.0) ** 2).mean()
+        mloss = F.binary_cross_entropy(wsum.clip(1e-5, 1.0 - 1e-5), mask)
+        loss = float(c["normal_weight"]) * normal_loss + float(c["mask_weight"]) * mloss + float(c["eikonal_weight"]) * eik
+        loss.backward()
+        with torch.no_grad():
+            m.grad[:m.n_small] = small.grad
+            m.grad[SMALL_PAD:] = table.grad
+            b.comp.view(n, P, 3).copy_(comp)
+            b.wsum.view(n, P).copy_(wsum[..., 0])
+            # the layout loss_terms() decodes: [mask_sum | normal * mask_sum | bce * n * 9 | eikonal * S * 9 | d loss / d inv_s ...]
+            b.stats[0] = mask_sum
+            b.stats[1] = normal_loss.detach() * mask_sum
+            b.stats[2] = mloss.detach() * (n * P)
+            b.stats[3] = eik.detach() * (S * P)
 
     def optimizer_step(self, presample_next: bool = False):
         """Adam (exp_runner.py:205-207).  After a lean forward_backward: ONE launch (snb_train_tail) that also unfolds the MLP
@@ -620,7 +733,10 @@ class FusedTrainer:
             batch = self.sample_batch()
         if jitter is None:
             jitter = torch.rand(self.n_patches, device=self.device, generator=self.gen)
-        self.forward_backward(batch, self.step_size(it), jitter, lean=self.lean)
+        if self.gradient_method == "ad":
+            self.forward_backward_ad(batch, self.step_size(it), jitter)
+        else:
+            self.forward_backward(batch, self.step_size(it), jitter, lean=self.lean)
         self.optimizer_step(presample_next=own and self.lean)
         self.iter_step += 1
         self.lr = self.conf["learning_rate"] * self._lr_factor()
@@ -756,7 +872,7 @@ class FusedTrainer:
         na = m.n_active
         if name == "snb_sdf_fwd_patch":      # write sdf (4 B) + kept features (4 B/level); read packed samples (12 B each)
             return M * (4 + 4 * na) + S * 12
-        if name == "snb_sdf_bwd_patch":      # read kept features (4 B/level) + positions' inputs + seeds (d_sdf0, d_sdf1); the table-gradient
+        if name in ("snb_sdf_bwd_patch", "snb_sdf_bwd_patch_ws"):      # read kept features (4 B/level) + positions' inputs + seeds (d_sdf0, d_sdf1); the table-gradient
             return M * (4 * na + 4) + 2 * P * S * 4   # reductions are L2 traffic (l2_bytes), SURVEY.md §8d
         if name in ("snb_train_optim", "snb_train_tail"):   # p, g, m, v read + p, m, v, g(zero) write + fp16 copy
             return (SMALL_PAD + 2 * m.offsets[na]) * (16 + 16) + 2 * m.offsets[na] * 2
@@ -771,7 +887,7 @@ class FusedTrainer:
         M, na = P * (S + E), self.model.n_active
         if name == "snb_sdf_fwd_patch":
             return M * na * 8 * 4
-        if name == "snb_sdf_bwd_patch":
+        if name in ("snb_sdf_bwd_patch", "snb_sdf_bwd_patch_ws"):
             return M * na * 8 * 8
         return None
 

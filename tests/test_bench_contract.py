@@ -25,9 +25,9 @@ def test_reference_arm_line():
     assert len(lines) == 1
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"].startswith("patch-rays/sec") and j["unit"] == "patch-rays/s"
-    assert j["higher_is_better"] is True and j["steps"] == 1 and j["value"] > 0 and j["ms_per_step"] > 0
+    assert j["higher_is_better"] is True and j["steps"] == 1 and j["warmup"] == 2 and j["value"] > 0 and j["ms_per_step"] > 0
     cb = j["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "64 patches" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "512 patches" in cb["sample"] and "16 levels" in cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in j["config"] and "model" not in j["config"]
 

@@ -223,11 +223,24 @@ def test_fused_forward_backward_vs_oracle(cuda, variance, cut_active, n_active, 
     m.net_grad.zero_()
     bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"], batch["v_inv"], batch["normal_gt"], batch["mask"])
     net = m.net_struct()
-    call("snb_sdf_bwd_patch", C.byref(bs), C.byref(net), C.byref(tr.buf.struct), ptr(tr.buf.feats), ptr(tr.buf.d_sdf0), ptr(tr.buf.d_sdf1),
-         ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
+    # what the trainer launches: beyond 4 live levels the split form (tcgen05 MLP backward -> workspace -> scatter kernel), else one kernel
+    call("snb_sdf_bwd_patch_ws", C.byref(bs), C.byref(net), C.byref(tr.buf.struct), ptr(tr.buf.feats), ptr(tr.buf.d_sdf0), ptr(tr.buf.d_sdf1),
+         ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad), ptr(tr.buf.bwd_ws), tr.buf.bwd_ws_bytes)
     tr.buf.stats[4] = 0.0
     call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(tr.buf.stats), ptr(m.grad))
     got = flat_grads()
+    if n_active > 4:
+        # cross-check of the two forms on identical inputs: the single fused kernel (no workspace) must give the same gradients up to
+        # fp32 summation order (the table sums the same TF32-rounded products in a different order; the MLP part is the same code)
+        split_table, split_net = m.grad[SMALL_PAD:].clone(), m.net_grad.clone()
+        m.grad.zero_()
+        m.net_grad.zero_()
+        call("snb_sdf_bwd_patch", C.byref(bs), C.byref(net), C.byref(tr.buf.struct), ptr(tr.buf.feats), ptr(tr.buf.d_sdf0), ptr(tr.buf.d_sdf1),
+             ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
+        fused_table, fused_net = m.grad[SMALL_PAD:], m.net_grad
+        assert (split_table - fused_table).abs().max().item() <= 2e-5 * fused_table.abs().max().item()
+        assert (split_net - fused_net).abs().max().item() <= 2e-5 * fused_net.abs().max().item()
+        assert ((split_table == 0) != (fused_table == 0)).sum().item() <= 8    # the same entries are touched (up to exact cancellations)
     # The tcgen05 backward forms d loss/d features (-> table) and dW0 / db0 from dz rounded to TF32 (round to
     # nearest: unbiased, 2^-12 rms relative per element -- the precision class of the fp16 dL/dy tiny-cuda-nn's own backward
     # consumes); sums over 64 hidden units / many points average that down.  z recompute, dW1, db1 are fp32-accurate.
@@ -313,7 +326,23 @@ def test_device_sampler_matches_dataset(cuda):
     assert cx.min() == 1 and cx.max() == ds.W - 3 and cy.min() == 1 and cy.max() == ds.H - 3    # whole range is reached
     o, d, pn, vinv, nrm, msk = ds.patches_at(view, cx, cy)
     near, far = ds.near_far_from_sphere(o[:, 1, 1], d[:, 1, 1])
-    assert torch.equal(b["normal_gt"], nrm.view(-1, 9, 3)) and torch.equal(b["mask"], msk.view(-1, 9)) and torch.equal(b["v_inv"], vinv.view(-1, 9, 9))
+    assert torch.equal(b["normal_gt"], nrm.view(-1, 9, 3)) and torch.equal(b["mask"], msk.view(-1, 9))
+    # V_inverse: the sampler's closed form (R A^-1, no table) against torch.inverse of [ray; right; down] (models/dataset_loader.py:126-137)
+    assert not tr.v_inverse_table
+    vref = vinv.view(-1, 9, 9)
+    assert (b["v_inv"] - vref).abs().max().item() <= 2e-5 * vref.abs().max().item()
+    eye = torch.einsum("nkab,nkbc->nkac", b["v_inv"].view(-1, 9, 3, 3),
+                       torch.stack([d.view(-1, 9, 3), R[:, None, :, 0].expand(-1, 9, 3), R[:, None, :, 1].expand(-1, 9, 3)], dim=-2))
+    assert (eye - torch.eye(3, device=cuda)).abs().max().item() < 1e-5       # V^-1 V = I on the sampler's own ray directions
+    # ... and the table path (SNB_VINV_TABLE=1: Dataset.V_inverse_all gathered per pixel) gives the table's bits
+    import ctypes as C
+    from supernormal_b200._lib import call
+    from supernormal_b200.trainer import SnbDataset
+    vtab = ds.V_inverse_all.to(cuda, torch.float32).contiguous()
+    ds_tab = SnbDataset(ds.n_images, ds.H, ds.W, len(ds.train_images), *[t.data_ptr() for t in tr._ds_tensors[:4]], vtab.data_ptr(), tr.train_ids.data_ptr())
+    call("snb_sample_patches", C.byref(ds_tab), tr.n_patches, tr.seed, 3, C.byref(tr._out_structs[tr._slot]))
+    assert torch.equal(tr.own_batch["v_inv"], vref) and torch.equal(tr.own_batch["rays_d"], b["rays_d"])
+    tr.sample_batch_device(3)
     assert torch.allclose(b["rays_d"], d.view(-1, 9, 3), atol=2e-6) and torch.equal(b["rays_o"], o[:, 1, 1]) and torch.equal(b["plane_n"], pn)
     ok = ~torch.isnan(near)
     assert torch.equal(torch.isnan(b["near"]), ~ok) and torch.allclose(b["near"][ok], near[ok], atol=1e-5) and torch.allclose(b["far"][ok], far[ok], atol=1e-5)
@@ -720,3 +749,54 @@ def test_checkpoint_interoperates_with_the_reference_format(cuda):
     assert inter >= 0.9 * min(a.grid.binary.sum().item(), b.grid.binary.sum().item())
     b.train_step()
     assert math.isfinite(b.loss_terms()["loss"])
+
+
+@pytest.mark.parametrize("n_active,enc", [(4, ENC), (9, ENC16)])
+def test_ad_gradient_method_vs_oracle(cuda, n_active, enc):
+    """gradient_method = 'ad' (models/renderer.py:225-226 + SDFNetwork.gradient, models/fields.py:107-119: analytic normals with
+    create_graph=True, i.e. a double backward through the MLP and the hash grid) in FusedTrainer against oracle.torch_ops with
+    grad = 'ad': same samples, rendered normals, loss terms and parameter gradients; then it trains."""
+    ds, osdf, odev, orend, tr_dfd, batch_cpu = _setup(cuda, n_active=n_active, ENC=enc)
+    from supernormal_b200.trainer import FusedTrainer
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene
+    tr = FusedTrainer(SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda), _conf(96, grad="ad", enc=enc), device=cuda,
+                      samples_per_ray_cap=256)
+    assert tr.gradient_method == "ad" and not tr.lean
+    tr.model.flat.copy_(tr_dfd.model.flat)
+    tr.model.refresh_table_f16()
+    tr.model.n_active = n_active
+    tr.grid._binary = tr_dfd.grid._binary.clone()
+    o, d, pn, vinv, nrm, msk = batch_cpu
+    batch, near, far = _to_gpu_batch(ds, batch_cpu, cuda)
+    step = 0.02
+    jitter = torch.rand(o.shape[0])
+    orend.sampling_step_size = step
+    out = orend.render(o, d, pn, near, far, vinv, jitter=jitter, gradient_method="ad")
+    loss, parts = T.losses(out, nrm, msk)
+    params = [osdf.encoding_params, osdf.lin0.weight_g, osdf.lin0.weight_v, osdf.lin0.bias, osdf.lin1.weight_g, osdf.lin1.weight_v,
+              osdf.lin1.bias, odev.variance]
+    loss.backward()
+    tr.forward_backward_ad(batch, step, jitter.to(cuda))
+    lt = tr.loss_terms()
+    assert lt["n_samples"] == out["n_samples"] and lt["overflow"] == 0
+    comp = tr.buf.comp.cpu().view(-1, 3, 3, 3)
+    assert (comp - out["comp_normal"]).abs().max() < 3e-3 * max(1.0, out["comp_normal"].abs().max().item())
+    for k, tol in (("normal", 3e-3), ("mask", 1e-3), ("eikonal", 3e-3)):
+        assert abs(lt[k] - float(parts[k])) <= tol * max(1.0, abs(float(parts[k]))), (k, lt[k], float(parts[k]))
+    m = tr.model
+    off = m._small_offsets()
+    g = m.grad.cpu()
+    got = {"table": g[2560:], "g0": g[off["g0"]:off["b0"]], "v0": g[off["v0"]:off["g0"]].view(64, m.d_in), "b0": g[off["b0"]:off["v1"]],
+           "g1": g[off["g1"]], "v1": g[off["v1"]:off["g1"]], "var": g[off["var"]]}
+    ref = {"table": params[0].grad, "g0": params[1].grad.flatten(), "v0": params[2].grad, "b0": params[3].grad, "g1": params[4].grad.flatten()[0],
+           "v1": params[5].grad.flatten(), "var": params[7].grad}
+    for k in ref:   # the oracle's features are fp16-rounded like ours; its double backward runs in fp32 torch ops on the same function
+        relk = (got[k] - ref[k]).norm().item() / max(ref[k].norm().item(), 1e-12)
+        assert relk <= 2e-2, (k, relk)
+    # ... and the whole step runs: sampler -> ad forward/backward -> fused Adam, loss finite and parameters moving
+    before = m.flat.clone()
+    tr.iter_step = 20      # past the lr = 0 first step
+    tr.lr = 5e-4
+    for _ in range(3):
+        tr.train_step()
+    assert math.isfinite(tr.loss_terms()["loss"]) and not torch.equal(before, m.flat)
