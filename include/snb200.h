@@ -219,7 +219,8 @@ int32_t snb_umma_selftest_lbo(const float *A, const float *B, float *D, int32_t 
  * without the autograd double pass.  sdf: f32[n] or null; grad: f32[n,3]. */
 int32_t snb_sdf_eval_grad(int64_t n, const float *x, const snb_net *h_net, float *sdf, float *grad, snb_stream_t stream);
 /* SDF at the 9 plane-projected rays of every sample start (+ own ends), keeping the encoded features.
- * sdf: [9*(capacity+end_capacity)]: starts at s*9+k, ends at 9*S + slot*9+k.  feats: half2 [points, n_levels] */
+ * sdf: [9*(capacity+end_capacity)]: starts at s*9+k, ends at 9*S + slot*9+k.  feats: half2 [points, 16] capacity; a row holds the live
+ * levels, row stride 1/2/4/8/16 half2 = n_active rounded up to a power of two (kept for snb_sdf_bwd_patch of the SAME n_active) */
 int32_t snb_sdf_fwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
                           float *sdf, void *feats, snb_stream_t stream);
 /* NeuS alpha -> patch transmittance scan -> dfd normals -> accumulation (models/renderer.py:164-267).
@@ -312,7 +313,7 @@ typedef struct snb_train_ctx { /* everything one training iteration touches; all
     float *flat_grad, *exp_avg, *exp_avg_sq;
     float *net_grad;          /* [SNB_NET_FLOATS] */
     float *sdf;               /* [9*(capacity+end_capacity)] */
-    void *feats;              /* half2 [9*(capacity+end_capacity), n_levels] */
+    void *feats;              /* half2 [9*(capacity+end_capacity), 16]: kept features, rows of 1/2/4/8/16 half2 (the live levels rounded up) */
     float *d_sdf0, *d_sdf1;   /* [9*capacity] */
     float *comp, *wsum, *dcomp, *dwsum; /* [N,9,3] [N,9] */
     float *stats;             /* [8] */

@@ -69,6 +69,13 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 2) sdf_eval_grad_kernel(int64_
     }
 }
 
+// row stride (in half2) of the kept-feature buffer: the live levels rounded up to a power of two (to an even count beyond 8), so that early in the schedule (1-2 live
+// levels) a point's row is 4-8 bytes instead of 4 * n_levels -- with the fixed 56-byte rows the backward read one 32-byte sector per point
+// for 4 useful bytes (15.9 MB DRAM per launch against 6.9 MB algorithmic, profiles/roofline_traffic.json of round 1)
+__host__ __device__ __forceinline__ uint32_t feat_row_stride(uint32_t n_active) {
+    return n_active <= 1 ? 1u : n_active <= 2 ? 2u : n_active <= 4 ? 4u : n_active <= 8 ? 8u : ((n_active + 1u) & ~1u);
+}
+
 struct PointRef {
     int s, k, patch;
     bool is_end;
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_fwd_patch_kernel(snb_pa
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t M = (int64_t)SNB_PATCH * (S + E);
-    const uint32_t L = net.meta.n_levels;
+    const uint32_t L = feat_row_stride(net.n_active);
     const int lane = threadIdx.x & 31;
     for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x; p0 < M; p0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = p0 + threadIdx.x;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
     const int tid = threadIdx.x, lane = tid & 31;
     const int S = sm.totals[0], E = sm.totals[1];
     const int64_t M = (int64_t)SNB_PATCH * (S + E);
-    const uint32_t L = net.meta.n_levels, n_active = net.n_active;
+    const uint32_t n_active = net.n_active, L = feat_row_stride(n_active);
     const int K = 4 + 2 * (int)n_active;  // live columns of the staged input: [1 | x y z | features of the active levels]
 
     // phase-B ownership: group g (64 threads) reduces points [64g, 64g+64); thread owns h in [4a,4a+4) and the live
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
     uint8_t *a1 = b2 + umma::tile_bytes(kN2, 64), *a2 = a1 + umma::tile_bytes(128, kK1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t L = net.meta.n_levels, n_active = net.n_active;
+    const uint32_t n_active = net.n_active, L = feat_row_stride(n_active);
 
     // ---- one-time staging: weights (TF32 hi / lo), level table, TMEM, barriers
     {
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(kMlpThreads, 2) sdf_bwd_mlp_umma_kernel(snb_pa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = warp >> 2, row = 32 * (warp & 3) + lane;      // this thread's point (row of the tiles, TMEM lane) and its half
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t L = net.meta.n_levels, n_active = net.n_active;
+    const uint32_t n_active = net.n_active, L = feat_row_stride(n_active);
 
     // ---- one-time staging: weights (TF32 hi / lo), TMEM, barriers
     {

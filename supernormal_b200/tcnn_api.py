@@ -144,6 +144,107 @@ class Encoding(torch.nn.Module):
         return f"n_input_dims={self.n_input_dims}, n_output_dims={self.n_output_dims}, seed={self.seed}, dtype={self.dtype}, hyperparams={self.encoding_config}"
 
 
+# ---- tcnn.Network / tcnn.NetworkWithInputEncoding (FullyFusedMLP / CutlassMLP configs) ------------------------------------------------
+# North-star API nicety ("optional"): SuperNormal itself never builds a tcnn network -- its SDF MLP is nn.Linear +
+# weight_norm + Softplus(beta=100) in fp32 (models/fields.py:37-70) and runs in the fused kernels of trainer.py.  These two modules exist so
+# that code written against tiny-cuda-nn's torch bindings (nerfacc's examples/radiance_fields/ngp.py:108-145) imports and runs on this
+# package.  They follow the bindings' conventions -- one flat fp32 `params`, no biases, input / output widths padded to multiples of 16,
+# Xavier-uniform init from `seed`, fp16 compute and fp16 output, `loss_scale` -- and evaluate the dense layers with torch's half-precision
+# GEMMs (cuBLAS: a plain library GEMM, not a hot path of this repo).
+_ACT = {
+    "none": lambda x: x, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh, "exponential": torch.exp,
+    "softplus": lambda x: torch.nn.functional.softplus(x * 10.0) / 10.0,          # tcnn: K_ACT = 10
+    "squareplus": lambda x: 0.5 * (x * 10.0 + torch.sqrt(x * x * 100.0 + 4.0)) / 10.0,
+    "sine": torch.sin, "leakyrelu": lambda x: torch.nn.functional.leaky_relu(x, 0.01),
+}
+
+
+def _pad16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+class Network(torch.nn.Module):
+    """tcnn.Network(n_input_dims, n_output_dims, network_config, seed=1337): a bias-free MLP with `n_hidden_layers` hidden layers of
+    `n_neurons` units.  params = [W_in (n_neurons x pad16(n_in)) | W_hidden ... | W_out (pad16(n_out) x n_neurons)], row-major."""
+
+    def __init__(self, n_input_dims: int, n_output_dims: int, network_config: Mapping, seed: int = 1337):
+        super().__init__()
+        cfg = dict(network_config)
+        otype = str(cfg.get("otype", "FullyFusedMLP")).lower()
+        if otype not in ("fullyfusedmlp", "cutlassmlp", "megakernelmlp"):
+            raise NotImplementedError(f"network otype {cfg.get('otype')!r}")
+        self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
+        self.n_neurons, self.n_hidden_layers = int(cfg.get("n_neurons", 64)), int(cfg.get("n_hidden_layers", 1))
+        if self.n_hidden_layers < 1:
+            raise ValueError("n_hidden_layers must be >= 1")
+        self.activation, self.output_activation = str(cfg.get("activation", "ReLU")).lower(), str(cfg.get("output_activation", "None")).lower()
+        for a in (self.activation, self.output_activation):
+            if a not in _ACT:
+                raise NotImplementedError(f"activation {a!r}")
+        self.network_config, self.seed = cfg, seed
+        self.padded_input, self.padded_output = _pad16(self.n_input_dims), _pad16(self.n_output_dims)
+        self._shapes = [(self.n_neurons, self.padded_input)] + [(self.n_neurons, self.n_neurons)] * (self.n_hidden_layers - 1) + \
+                       [(self.padded_output, self.n_neurons)]
+        g = torch.Generator().manual_seed(seed)
+        chunks = []
+        for fo, fi in self._shapes:      # xavier_uniform over the padded matrix, like tcnn's initialize_params
+            bound = (6.0 / (fi + fo)) ** 0.5
+            chunks.append((torch.rand(fo * fi, generator=g) * 2.0 - 1.0) * bound)
+        self.params = torch.nn.Parameter(torch.cat(chunks))
+        self.loss_scale = 128.0
+        self.dtype = torch.float16
+
+    def _weights(self, params: Tensor):
+        out, off = [], 0
+        for fo, fi in self._shapes:
+            out.append(params[off:off + fo * fi].view(fo, fi))
+            off += fo * fi
+        return out
+
+    def mlp(self, x: Tensor, params: Tensor) -> Tensor:
+        """x [N, n_input_dims] (any float dtype) -> fp16 [N, n_output_dims]"""
+        h = x.to(torch.float16)
+        if self.padded_input != self.n_input_dims:
+            h = torch.nn.functional.pad(h, (0, self.padded_input - self.n_input_dims), value=1.0)   # tcnn pads inputs with ones
+        ws = self._weights(params)
+        for w in ws[:-1]:
+            h = _ACT[self.activation](torch.nn.functional.linear(h, w.to(torch.float16)))
+        y = _ACT[self.output_activation](torch.nn.functional.linear(h, ws[-1].to(torch.float16)))
+        return y[:, :self.n_output_dims]
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        return self.mlp(x, self.params)
+
+    def extra_repr(self):
+        return f"n_input_dims={self.n_input_dims}, n_output_dims={self.n_output_dims}, seed={self.seed}, dtype={self.dtype}, hyperparams={self.network_config}"
+
+
+class NetworkWithInputEncoding(torch.nn.Module):
+    """tcnn.NetworkWithInputEncoding(n_input_dims, n_output_dims, encoding_config, network_config, seed=1337): HashGrid encoding ->
+    Network, ONE flat parameter vector params = [network | encoding] (the order of tiny-cuda-nn's NetworkWithInputEncoding::set_params)."""
+
+    def __init__(self, n_input_dims: int, n_output_dims: int, encoding_config: Mapping, network_config: Mapping, seed: int = 1337):
+        super().__init__()
+        enc = Encoding(n_input_dims, encoding_config, seed=seed)
+        net = Network(enc.n_output_dims, n_output_dims, network_config, seed=seed)
+        self.n_input_dims, self.n_output_dims, self.seed = int(n_input_dims), int(n_output_dims), seed
+        self._n_net = net.params.numel()
+        self.params = torch.nn.Parameter(torch.cat([net.params.detach(), enc.params.detach()]))
+        del enc._parameters["params"], net._parameters["params"]     # the flat vector above is the only parameter (checkpoints, optimizers)
+        object.__setattr__(self, "_enc", enc)                        # helper objects, deliberately not registered sub-modules
+        object.__setattr__(self, "_net", net)
+        self.loss_scale, self.dtype = 128.0, torch.float16
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        p_net, p_enc = self.params[:self._n_net], self.params[self._n_net:]
+        feat = _Encode.apply(self._enc, x.to(torch.float).contiguous(), p_enc.contiguous())
+        return self._net.mlp(feat, p_net)
+
+
 def install_as_tinycudann():
     """Register this module as `tinycudann` (and nerfacc_api as `nerfacc`) in sys.modules so the
     reference's models/fields.py / models/renderer.py import unmodified."""

@@ -252,7 +252,7 @@ class SampleBuffers:
         self.scratch_t1 = torch.zeros(n_patches * scratch_stride, **f32)
         m_cap = P * (self.capacity + self.end_capacity)
         self.sdf = torch.zeros(m_cap, **f32)
-        self.feats = torch.zeros(m_cap * n_levels * 2, dtype=torch.float16, device=device)
+        self.feats = torch.zeros(m_cap * 16 * 2, dtype=torch.float16, device=device)   # rows of feat_row_stride(n_active) <= 16 half2 (fused_sdf.cu)
         self.d_sdf0 = torch.zeros(P * self.capacity, **f32)
         self.d_sdf1 = torch.zeros(P * self.capacity, **f32)
         self.comp = torch.zeros(n_patches, P, 3, **f32)

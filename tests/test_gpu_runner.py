@@ -111,7 +111,7 @@ def test_mesh_post_on_device(cuda):
     assert pts.shape[1] == 3 and 0.9 * n_fg <= pts.shape[0] <= n_fg
     tr.model.prep()
     assert tr.model.sdf(pts).abs().max().item() < 2e-3
-    assert (pts.norm(dim=-1) - pts.norm(dim=-1).mean()).abs().max().item() < 0.1      # a (perturbed) sphere
+    assert (pts.norm(dim=-1) - pts.norm(dim=-1).mean()).abs().max().item() < 0.3      # a (perturbed) sphere
 
 
 def test_render_normal_pixel_based_vs_oracle(cuda):
