@@ -42,9 +42,10 @@ def replicas_identical(tr):
     return all(torch.equal(all_sig[0], s) for s in all_sig)
 
 
-out = {"world": world, "peer_f16_only": os.environ.get("SNB_PEER_F16ONLY", "0")}
+out = {"world": world}
 A, B = make("peer"), make("nccl")
 out["peer_mode"] = [A.peer_mode, B.peer_mode]
+out["peer_f16_only"] = bool(getattr(A.model, "peer_f16_only", False))
 ident, close, losses = [], [], []
 for it in range(a.check_steps):
     A.train_step()

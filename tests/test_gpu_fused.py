@@ -800,3 +800,26 @@ def test_ad_gradient_method_vs_oracle(cuda, n_active, enc):
     for _ in range(3):
         tr.train_step()
     assert math.isfinite(tr.loss_terms()["loss"]) and not torch.equal(before, m.flat)
+
+
+def test_adam_step_is_invariant_to_the_gradient_scale(cuda):
+    """Data-parallel gradients are AVERAGED over the ranks (grad_scale = 1 / world in snb_train_tail_peer / snb_train_optim).  With Adam
+    that choice is immaterial: m / sqrt(v) is invariant to a constant gradient scale, only eps = 1e-8 sees it -- summing instead of
+    averaging over 8 ranks moves no parameter by more than a few 1e-3 of one learning-rate step.  (The quality shift of the weak-scaling
+    runs is therefore the 8x larger batch at unchanged lr / iteration count, not the normalisation: DESIGN.md section 6.)"""
+    from supernormal_b200._lib import call, ptr
+    n = 200003
+    torch.manual_seed(0)
+    p0 = torch.randn(n, device=cuda)
+    lr = 5e-4
+    outs = []
+    for scale in (1.0, 1.0 / 8.0):
+        p, m, v = p0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+        for t in range(1, 9):
+            gen = torch.Generator(device=cuda).manual_seed(t)     # |g| in [0.75e-3, 1.25e-3] (typical table-gradient size), random sign: bounded away
+            g = (torch.rand(n, device=cuda, generator=gen) * 0.5 + 0.75) * 1e-3 * torch.sign(torch.randn(n, device=cuda, generator=gen))   # from eps
+            call("snb_adam_step", n, ptr(p), ptr(g), ptr(m), ptr(v), None, lr, 0.9, 0.999, 1e-8, t, scale)
+        outs.append(p)
+    moved = (outs[0] - p0).abs().mean().item()
+    assert moved > 0.5 * lr                                                     # the parameters did move ~ lr per step
+    assert (outs[0] - outs[1]).abs().max().item() < 5e-3 * lr * 8               # ... identically for both scales, up to eps
