@@ -123,7 +123,7 @@ __device__ __forceinline__ void layer0(float x, float y, float z, const __half2 
     rank1_update(acc, s_net + kOffW0T + 0 * kH, x);
     rank1_update(acc, s_net + kOffW0T + 1 * kH, y);
     rank1_update(acc, s_net + kOffW0T + 2 * kH, z);
-    for (uint32_t l = 0; l < n_active; ++l) {
+    for (uint32_t l = 0; l < n_active; ++l) {   // (unrolling by 2 for more gathers in flight spills: 64 accumulators per thread)
         __half2 f;
         if (LOAD_FEAT) {
             f = feat_row[l];

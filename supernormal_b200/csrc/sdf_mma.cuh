@@ -170,6 +170,9 @@ __device__ __forceinline__ float warp_sdf_mma(bool valid, float x, float y, floa
     const int ksteps = (int)(2 * n_active + 7) >> 3;
     float *row = xs + lane * kXsStride;
     __syncwarp();
+    // two levels per iteration: 16 independent table gathers in flight per lane instead of 8 (the kernel is gather-latency bound:
+    // 29 % of its stall samples sit on the HFMA2 that consumes the loads, profiles/r02_sass_hist_step_it4800.txt)
+#pragma unroll 2
     for (uint32_t l = 0; l < n_active; ++l) {
         float2 ff = make_float2(0.f, 0.f);
         if (valid) {
