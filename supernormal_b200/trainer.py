@@ -241,7 +241,9 @@ class SampleBuffers:
         self.end_counts = torch.zeros(n_patches, **i32)
         self.packed_info = torch.zeros(n_patches, 2, **i32)
         self.end_packed = torch.zeros(n_patches, 2, **i32)
-        self.totals = torch.zeros(4, **i32)
+        # loss accumulators (8 f32) and sample totals (4 i32) share ONE 48-byte allocation: the host-fed path reads both back with one D2H copy
+        self.stats_totals = torch.zeros(12, **i32)
+        self.totals = self.stats_totals[8:12]
         self.t0 = torch.zeros(self.capacity, **f32)
         self.t1 = torch.zeros(self.capacity, **f32)
         self.patch_idx = torch.zeros(self.capacity, **i32)
@@ -259,7 +261,7 @@ class SampleBuffers:
         self.wsum = torch.zeros(n_patches, P, **f32)
         self.dcomp = torch.zeros(n_patches, P, 3, **f32)
         self.dwsum = torch.zeros(n_patches, P, **f32)
-        self.stats = torch.zeros(8, **f32)
+        self.stats = self.stats_totals[:8].view(torch.float32)
         # workspace of the split backward (snb_sdf_bwd_patch_ws): positions + d loss / d features of every point, [level][ray][sample]
         self.bwd_ws_bytes = int(_lib.lib().snb_sdf_bwd_workspace_bytes(n_levels, self.capacity, self.end_capacity))
         self.bwd_ws = torch.empty(self.bwd_ws_bytes, dtype=torch.uint8, device=device)
@@ -298,8 +300,7 @@ class HostBatchFeeder:
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [torch.cuda.Event() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=tr.device)
-        self.log_f = torch.zeros(log_capacity, 8, dtype=torch.float32).pin_memory()
-        self.log_i = torch.zeros(log_capacity, 4, dtype=torch.int32).pin_memory()
+        self.log = torch.zeros(log_capacity, 12, dtype=torch.int32).pin_memory()      # per step: stats[8] (f32 bits) | totals[4]
         self.n_fed = self.n_run = 0
 
     def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -346,9 +347,8 @@ class HostBatchFeeder:
         cur.wait_event(self.ready[slot])
         dv = self._views(self.dev[slot])
         tr.train_step(batch={k: dv[k] for k in BATCH_KEYS}, jitter=dv["jitter"])
-        i = self.n_run % self.log_f.shape[0]
-        self.log_f[i].copy_(tr.buf.stats, non_blocking=True)
-        self.log_i[i].copy_(tr.buf.totals, non_blocking=True)
+        i = self.n_run % self.log.shape[0]
+        self.log[i].copy_(tr.buf.stats_totals, non_blocking=True)     # ONE 48-byte device -> host copy per step
         self.free[slot].record(cur)
         self.n_run += 1
 
@@ -357,9 +357,9 @@ class HostBatchFeeder:
         torch.cuda.current_stream(self.tr.device).synchronize()
         c, tr = self.tr.conf, self.tr
         out = []
-        cap = self.log_f.shape[0]
+        cap = self.log.shape[0]
         for i in range(max(0, self.n_run - cap), self.n_run):
-            r, t = self.log_f[i % cap].tolist(), self.log_i[i % cap].tolist()
+            r, t = self.log[i % cap, :8].view(torch.float32).tolist(), self.log[i % cap, 8:].tolist()
             S = max(t[0], 1)
             normal, mask, eik = r[1] / r[0], r[2] / (tr.n_patches * P), r[3] / (S * P)
             out.append(dict(loss=c["normal_weight"] * normal + c["mask_weight"] * mask + c["eikonal_weight"] * eik, normal=normal,
