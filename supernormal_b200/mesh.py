@@ -74,7 +74,10 @@ def extract_geometry(model, bound_min, bound_max, resolution: int, threshold: fl
     model.prep()
     c0, c1 = dp.slab_cells(resolution, rank, world)
     parts = []
-    n_sub = max(1, min(slabs, c1 - c0))
+    # the marching-cubes kernels number potential edge vertices with int32 ids (3 per lattice point of a slab): split this rank's range into
+    # enough sequential slabs on its own (1024^3 -- own_objects.conf's val_mesh_res -- needs 2 on one GPU)
+    need = -(-(3 * (c1 - c0 + 1) * resolution * resolution) // (2 ** 31 - 1))
+    n_sub = max(1, min(max(slabs, need), c1 - c0))
     for s in range(n_sub):
         a = c0 + (c1 - c0) * s // n_sub
         b = c0 + (c1 - c0) * (s + 1) // n_sub
