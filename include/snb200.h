@@ -376,6 +376,11 @@ typedef struct snb_peer_group {
     uint32_t epoch;         /* value the two in-kernel barriers wait for: must grow strictly from launch to launch of one peer
                              * group, whatever the optimizer step count does (a resume rewinds step_count, not this).  0: use
                              * step_count (a run that never rewinds). */
+    uint64_t *trace;        /* optional (may be NULL): device buffer u64[trace_capacity][4]; block 0 of launch `epoch` stores %globaltimer
+                             * (ns, this GPU's clock) at: kernel start | every rank's "backward complete" flag seen | local chunk
+                             * blocks done (reduce + Adam + broadcast fenced) | every rank's "stores done" flag seen -- the in-kernel
+                             * timeline of the two cross-GPU barriers (scripts/dp_peer_trace.py) */
+    int32_t trace_capacity;
 } snb_peer_group;
 int32_t snb_train_tail_peer(const snb_train_ctx *h_ctx, const snb_peer_group *h_peers, float lr, int32_t step_count,
                             const snb_dataset *h_ds_next, int32_t n_patches_next, uint64_t seed, uint64_t next_step,

@@ -297,6 +297,8 @@ struct PeerArgs {
     uint32_t *counter;            // local
     uint32_t epoch;
     int n_adam_blocks;
+    unsigned long long *trace;   // optional u64[trace_cap][4] timeline of block 0 (snb_peer_group.trace)
+    int trace_cap;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -403,6 +405,8 @@ __global__ void __launch_bounds__(kTailThreads, 1) train_tail_peer_kernel(const 
     __shared__ float s_norm[kH], s_red[4];
     const SmallLayout L(a.n_levels);
     const int lane = tid & 31, warp = tid >> 5;
+    unsigned long long *tr = (pg.trace && pg.trace_cap > 0) ? pg.trace + 4ull * (pg.epoch % (uint32_t)pg.trace_cap) : nullptr;
+    if (tid == 0 && tr) tr[0] = global_ns();
     if (tid == 0) {
         a.g[kOffInvS] = a.stats[4];   // the inv_s gradient of this rank travels in the free slot of the folded-gradient block
         __threadfence_system();
@@ -419,6 +423,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) train_tail_peer_kernel(const 
         vr[k] = in ? a.v[e] : 0.f;
     }
     wait_flags(my_flags, my_flags + 16, pg.world, pg.epoch, 200);
+    if (tid == 0 && tr) tr[1] = global_ns();
 #pragma unroll
     for (int k = 0; k < kSmallIters; ++k) {
         const int e = tid + k * kTailThreads;
@@ -483,10 +488,12 @@ __global__ void __launch_bounds__(kTailThreads, 1) train_tail_peer_kernel(const 
         }
         *pg.counter = 0u;
         __threadfence_system();
+        if (tr) tr[2] = global_ns();
     }
     __syncthreads();
     if (tid < pg.world) st_release_sys(pg.flags[tid] + kMaxPeers + pg.rank, pg.epoch);
     wait_flags(my_flags + kMaxPeers, my_flags + 16, pg.world, pg.epoch, 400);
+    if (tid == 0 && tr) tr[3] = global_ns();
     for (int e = tid; e < kNetFloats; e += kTailThreads) a.g[e] = 0.f;   // every rank has read this block: ready for the next backward
 }
 
@@ -639,6 +646,8 @@ extern "C" int32_t snb_train_tail_peer(const snb_train_ctx *c, const snb_peer_gr
     }
     pa.counter = pgrp->counter;
     pa.epoch = pgrp->epoch ? pgrp->epoch : (uint32_t)step_count;
+    pa.trace = (unsigned long long *)pgrp->trace;
+    pa.trace_cap = pgrp->trace_capacity;
     // one CTA per SM at most (every waiting CTA is resident): block 0 + sampler blocks + chunk blocks <= 148
     const int64_t n_chunks = cdiv(a.n_live / 4, (int64_t)kTailThreads);
     int64_t own_chunks = cdiv(n_chunks, (int64_t)pgrp->world);

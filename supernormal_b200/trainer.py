@@ -65,7 +65,7 @@ class SnbTrainCtx(C.Structure):
 class SnbPeerGroup(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("param", C.c_void_p * dp.MAX_PEERS), ("grad", C.c_void_p * dp.MAX_PEERS),
                 ("table_f16", C.c_void_p * dp.MAX_PEERS), ("flags", C.c_void_p * dp.MAX_PEERS), ("counter", C.c_void_p),
-                ("table_f16_only", C.c_int32), ("epoch", C.c_uint32)]
+                ("table_f16_only", C.c_int32), ("epoch", C.c_uint32), ("trace", C.c_void_p), ("trace_capacity", C.c_int32)]
 
 
 class SDFModel:
@@ -157,8 +157,11 @@ class SDFModel:
     def peer_struct(self) -> SnbPeerGroup:
         pg, o = self.peer, self.peer_offsets
         arr = lambda off: (C.c_void_p * dp.MAX_PEERS)(*(pg.ptrs(off) + [None] * (dp.MAX_PEERS - pg.world)))
+        # SNB_PEER_TRACE=n: keep the in-kernel timeline (4 globaltimer stamps of block 0) of the last n peer-tail launches (scripts/dp_peer_trace.py)
+        n_trace = int(os.environ.get("SNB_PEER_TRACE", "0"))
+        self.peer_trace = torch.zeros(max(n_trace, 1), 4, dtype=torch.int64, device=self.device) if n_trace > 0 else None
         return SnbPeerGroup(pg.world, pg.rank, arr(o[0]), arr(o[1]), arr(o[2]), arr(o[3]), self.peer_counter.data_ptr(),
-                            int(self.peer_f16_only))
+                            int(self.peer_f16_only), 0, None if self.peer_trace is None else self.peer_trace.data_ptr(), n_trace)
 
     @torch.no_grad()
     def gather_table(self) -> torch.Tensor:
@@ -241,9 +244,11 @@ class SampleBuffers:
         self.end_counts = torch.zeros(n_patches, **i32)
         self.packed_info = torch.zeros(n_patches, 2, **i32)
         self.end_packed = torch.zeros(n_patches, 2, **i32)
-        # loss accumulators (8 f32) and sample totals (4 i32) share ONE 48-byte allocation: the host-fed path reads both back with one D2H copy
-        self.stats_totals = torch.zeros(12, **i32)
-        self.totals = self.stats_totals[8:12]
+        # loss accumulators (8 f32) and sample totals (4 i32) share ONE 48-byte allocation: the host-fed path reads both back with one D2H
+        # copy.  Two such sets: HostBatchFeeder alternates them step by step (flip()), so the read-back of step i can run on a side stream
+        # while step i + 1 already resets / accumulates into the other set.  Everything else uses set 0 throughout.
+        self._sets = [torch.zeros(12, **i32) for _ in range(2)]
+        self.set_idx = 0
         self.t0 = torch.zeros(self.capacity, **f32)
         self.t1 = torch.zeros(self.capacity, **f32)
         self.patch_idx = torch.zeros(self.capacity, **i32)
@@ -261,13 +266,32 @@ class SampleBuffers:
         self.wsum = torch.zeros(n_patches, P, **f32)
         self.dcomp = torch.zeros(n_patches, P, 3, **f32)
         self.dwsum = torch.zeros(n_patches, P, **f32)
-        self.stats = self.stats_totals[:8].view(torch.float32)
         # workspace of the split backward (snb_sdf_bwd_patch_ws): positions + d loss / d features of every point, [level][ray][sample]
         self.bwd_ws_bytes = int(_lib.lib().snb_sdf_bwd_workspace_bytes(n_levels, self.capacity, self.end_capacity))
         self.bwd_ws = torch.empty(self.bwd_ws_bytes, dtype=torch.uint8, device=device)
-        self.struct = SnbSamples(self.capacity, self.end_capacity, scratch_stride, *[t.data_ptr() for t in (
-            self.counts, self.end_counts, self.packed_info, self.end_packed, self.totals, self.t0, self.t1,
-            self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1)])
+        self._structs = [SnbSamples(self.capacity, self.end_capacity, scratch_stride, *[t.data_ptr() for t in (
+            self.counts, self.end_counts, self.packed_info, self.end_packed, st[8:12], self.t0, self.t1,
+            self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1)]) for st in self._sets]
+
+    # the current accumulator set (see __init__)
+    @property
+    def stats_totals(self) -> torch.Tensor:
+        return self._sets[self.set_idx]
+
+    @property
+    def stats(self) -> torch.Tensor:
+        return self._sets[self.set_idx][:8].view(torch.float32)
+
+    @property
+    def totals(self) -> torch.Tensor:
+        return self._sets[self.set_idx][8:12]
+
+    @property
+    def struct(self) -> SnbSamples:
+        return self._structs[self.set_idx]
+
+    def flip(self) -> None:
+        self.set_idx ^= 1
 
 
 BATCH_KEYS = ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")
@@ -300,6 +324,9 @@ class HostBatchFeeder:
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.free = [torch.cuda.Event() for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=tr.device)
+        self.d2h_stream = torch.cuda.Stream(device=tr.device)      # loss read-backs: never in front of a batch copy, never inside the compute stream
+        self.step_done = [torch.cuda.Event() for _ in range(2)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(2)]
         self.log = torch.zeros(log_capacity, 12, dtype=torch.int32).pin_memory()      # per step: stats[8] (f32 bits) | totals[4]
         self.n_fed = self.n_run = 0
 
@@ -346,15 +373,23 @@ class HostBatchFeeder:
         cur = torch.cuda.current_stream(tr.device)
         cur.wait_event(self.ready[slot])
         dv = self._views(self.dev[slot])
-        tr.train_step(batch={k: dv[k] for k in BATCH_KEYS}, jitter=dv["jitter"])
+        tr.buf.flip()                                   # this step accumulates into the set the step before last used ...
+        k = tr.buf.set_idx
+        cur.wait_event(self.d2h_done[k])                # ... whose read-back (two steps ago) must have left the device
+        tr.train_step(batch={k_: dv[k_] for k_ in BATCH_KEYS}, jitter=dv["jitter"])
+        self.step_done[k].record(cur)
         i = self.n_run % self.log.shape[0]
-        self.log[i].copy_(tr.buf.stats_totals, non_blocking=True)     # ONE 48-byte device -> host copy per step
+        with torch.cuda.stream(self.d2h_stream):        # ONE 48-byte device -> host copy per step, off the compute stream
+            self.d2h_stream.wait_event(self.step_done[k])
+            self.log[i].copy_(tr.buf.stats_totals, non_blocking=True)
+            self.d2h_done[k].record(self.d2h_stream)
         self.free[slot].record(cur)
         self.n_run += 1
 
     def losses(self) -> List[Dict[str, float]]:
         """Synchronise and decode the logged loss terms of the last min(n_run, log_capacity) steps."""
         torch.cuda.current_stream(self.tr.device).synchronize()
+        self.d2h_stream.synchronize()
         c, tr = self.tr.conf, self.tr
         out = []
         cap = self.log.shape[0]
