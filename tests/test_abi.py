@@ -59,3 +59,30 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
     for name, ct in pairs.items():
         assert int(out[name]) == C.sizeof(ct), (name, out[name], C.sizeof(ct))
+
+
+def test_sample_buffers_accumulator_sets_and_workspace_size():
+    """Host logic of trainer.SampleBuffers (no kernel runs): the two loss-accumulator / totals sets alias one 48-byte allocation each, the
+    sample struct of a set points at ITS totals, flip() switches both, and the split backward's workspace has the size the C ABI asks for."""
+    import ctypes as C
+    import torch
+    from supernormal_b200 import _lib
+    from supernormal_b200.trainer import P, SampleBuffers
+    b = SampleBuffers(n_patches=64, samples_per_ray_cap=16, scratch_stride=128, n_levels=14, device="cpu")
+    assert b.capacity == 64 * 16 and b.end_capacity == max(64 * 8, b.capacity // 4)
+    need = _lib.lib().snb_sdf_bwd_workspace_bytes(14, b.capacity, b.end_capacity)
+    assert b.bwd_ws_bytes == need == P * (b.capacity + b.end_capacity) * (16 + 14 * 8) and b.bwd_ws.numel() == need
+    assert _lib.lib().snb_sdf_bwd_workspace_bytes(0, 1, 1) == -1 and _lib.lib().snb_sdf_bwd_workspace_bytes(17, 1, 1) == -1
+    for k in (0, 1):
+        assert b.set_idx == k
+        st = b.stats_totals
+        assert st.numel() == 12 and st.dtype == torch.int32
+        assert b.stats.data_ptr() == st.data_ptr() and b.stats.dtype == torch.float32 and b.stats.numel() == 8
+        assert b.totals.data_ptr() == st.data_ptr() + 32 and b.totals.numel() == 4
+        assert b.struct.totals == b.totals.data_ptr() and b.struct.capacity == b.capacity
+        b.stats[3] = 2.5
+        b.totals[1] = 7
+        assert st[3:4].view(torch.float32).item() == 2.5 and st[9].item() == 7
+        b.flip()
+    assert b.set_idx == 0 and b._sets[0].data_ptr() != b._sets[1].data_ptr()
+    assert b.feats.numel() == P * (b.capacity + b.end_capacity) * 16 * 2        # rows of up to 16 half2
