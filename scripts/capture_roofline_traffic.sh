@@ -22,8 +22,8 @@ for r in rows[2:]:
     names.add(d["Kernel Name"].split("(")[0])
 out = {"entry_point": "snb_sdf_bwd_patch_ws", "kernel": sorted(names), "launches": n, "dram_bytes_per_launch": tot / max(n, 1),
        "command": "ncu --set full --clock-control none --profile-from-start off -k regex:sdf_bwd_patch_umma_kernel -c 6 python bench.py --steps 20 --warmup 5 (timed region only)",
-       "note": f"mean of {n} launches inside the driver's window (iterations 5-25, 1 live level), ncu --set full --clock-control none; beyond the algorithmic bytes: "
-               "first-touch reads of the fp32 gradient-table lines the L2 reductions land on"}
+       "note": f"mean of {n} launches inside the driver's window (iterations 5-25, 1 live level), ncu --set full --clock-control none; inputs written by the "
+               "forward / render kernels of the same step are mostly still L2-resident, so this can sit below the algorithmic bytes"}
 json.dump(out, open("gpurun_out/roofline_traffic.json", "w"), indent=1)
 print(json.dumps(out))
 PY

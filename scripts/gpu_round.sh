@@ -1,17 +1,18 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list (+ optional full capture of one kernel).
+# One GPU-box visit in the driver's order: parity tests, smoke, the reference arm and our arm of bench.py as the driver launches them.
 set -u
 mkdir -p gpurun_out
 make -s -C oracle
-python -m pytest tests -m gpu -q 2>&1 | grep -E "passed|failed|^E  |Error|^FAILED" | head -60
-python bench.py --steps ${STEPS:-400} --warmup ${WARMUP:-20} ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench.json
-if [ "${NCU:-1}" = "1" ]; then
-  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -s ${NCU_SKIP:-0} -c ${NCU_COUNT:-400} --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 60 --warmup ${NCU_WARMUP:-3} --no-cpu --e2e-steps 1 --ref-cuda-steps 0 > gpurun_out/ncu_bench.log 2>&1
-  python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launches_summary.txt
-fi
-if [ -n "${NCU_KERNEL:-}" ]; then
-  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${NCU_KERNEL} -s ${NCU_KSKIP:-20} -c 2 -o gpurun_out/prof_${NCU_KERNEL} \
-      python bench.py --steps 60 --warmup ${NCU_WARMUP:-3} --no-cpu --e2e-steps 1 --ref-cuda-steps 0 > gpurun_out/ncu_full.log 2>&1
-  ncu -i gpurun_out/prof_${NCU_KERNEL}.ncu-rep --page raw --csv 2>/dev/null | python scripts/summarize_ncu_raw.py | tee gpurun_out/prof_${NCU_KERNEL}.txt
-fi
+python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --impl reference --gpus 1 --steps ${STEPS:-20} --warmup ${WARMUP:-5} > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference arm rc=$?"; cut -c1-400 gpurun_out/bench_reference.json
+python bench.py --gpus 1 --steps ${STEPS:-20} --warmup ${WARMUP:-5} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "our arm rc=$?"
+python - <<'PY'
+import json
+j = json.load(open("gpurun_out/bench.json"))
+for k in ("value", "ms_per_step", "e2e", "continuation", "time_to_mesh", "schedule_avg", "roofline", "roofline_l2_reduction", "cpu_baseline", "gpu_launches", "clocks", "dtype"):
+    print(k, json.dumps(j.get(k))[:420])
+for k in ("reference_cuda_path", "dropin_api_path"):
+    r = j.get(k) or {}
+    print(k, r.get("ms_per_step"), r.get("ours_ms_per_step_same_window"))
+PY

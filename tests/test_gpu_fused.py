@@ -823,3 +823,29 @@ def test_adam_step_is_invariant_to_the_gradient_scale(cuda):
     moved = (outs[0] - p0).abs().mean().item()
     assert moved > 0.5 * lr                                                     # the parameters did move ~ lr per step
     assert (outs[0] - outs[1]).abs().max().item() < 5e-3 * lr * 8               # ... identically for both scales, up to eps
+
+
+@pytest.mark.parametrize("n_active", [2, 7])
+def test_step_with_no_samples_is_a_clean_no_op(cuda, n_active):
+    """Every centre ray in the zero region of the occupancy grid (models/renderer.py:137-140: the reference returns early and skips the
+    optimizer step): the fused step must run through with S = 0 -- both backward forms, the tail kernel -- leave no NaN behind, produce zero
+    gradients and, with fresh Adam moments, leave every parameter bit-identical.  NaN near / far (rays missing the unit sphere,
+    models/dataset_loader.py:294-296) are part of the same batch."""
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    tr = FusedTrainer(ds, dict(DILIGENT_CONF, batch_size=128, end_iter=400, increase_bindwidth_every=10 ** 6), device=cuda)
+    tr.iter_step = 101                       # not a multiple of the occupancy / bandwidth periods: the grid below stays as set
+    tr.lr = 5e-4
+    tr.model.n_active = n_active
+    tr.grid._binary.zero_()
+    before = tr.model.flat.clone()
+    batch, jitter = tr.sample_batch_device(101)
+    assert torch.isnan(batch["near"]).any()   # corner patches miss the unit sphere
+    for _ in range(2):
+        tr.train_step()
+    lt = tr.loss_terms()
+    assert lt["n_samples"] == 0 and lt["n_ends"] == 0 and lt["overflow"] == 0
+    assert math.isfinite(lt["loss"]) and lt["eikonal"] == 0.0
+    assert torch.equal(tr.model.flat, before) and (tr.model.grad == 0).all() and torch.isfinite(tr.model.net).all()
+    assert (tr.buf.comp == 0).all() and (tr.buf.wsum == 0).all()
