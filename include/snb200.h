@@ -259,6 +259,21 @@ int64_t snb_sdf_bwd_workspace_bytes(int32_t n_levels, int64_t capacity, int64_t 
 int32_t snb_sdf_bwd_patch_ws(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
                              const void *feats, const float *d_sdf0, const float *d_sdf1, float *table_grad,
                              float *net_grad, void *workspace, int64_t workspace_bytes, snb_stream_t stream);
+/* gradient_method = 'ad' (models/renderer.py:225-226; SDFNetwork.gradient with create_graph=True, models/fields.py:107-119) inside the fused
+ * step, without autograd:
+ *   snb_sdf_grad_patch      analytic d sdf / d x at every sample start of every in-patch ray (point p = 9 s + k), f32 [9 * capacity, 3]
+ *   snb_render_fused_ad     snb_render_fused with those gradients as the per-sample normals; d_grad = d loss / d gradient (same layout),
+ *                           d_sdf0 / d_sdf1 = the alpha path only
+ *   snb_sdf_grad_bwd_patch  parameter gradients of d_grad . grad_x sdf -- the double backward through MLP and hash grid (table: value-weight
+ *                           term through sigmoid', derivative-weight term through the tangent) -- accumulated like snb_sdf_bwd_patch
+ *   snb_train_fwd_bwd_lean_ad  the lean iteration with these three in place of the dfd render / backward */
+int32_t snb_sdf_grad_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples, float *grad,
+                           snb_stream_t stream);
+int32_t snb_render_fused_ad(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples, const float *sdf,
+                            const float *grad_in, float normal_weight, float mask_weight, float eikonal_weight, float *comp,
+                            float *wsum, float *d_sdf0, float *d_sdf1, float *d_grad, float *stats, snb_stream_t stream);
+int32_t snb_sdf_grad_bwd_patch(const snb_patch_batch *h_batch, const snb_net *h_net, const snb_samples *h_samples,
+                               const void *feats, const float *d_grad, float *table_grad, float *net_grad, snb_stream_t stream);
 /* Un-fold net_grad into gradients of (v,g,b,variance) (weight_norm / exp backward), in `small` layout. */
 int32_t snb_unfold_grads(int32_t n_levels, const float *small, const float *net_grad, const float *stats,
                          float *small_grad, snb_stream_t stream);
@@ -338,6 +353,10 @@ int32_t snb_train_optim(const snb_train_ctx *h_ctx, float lr, int32_t step_count
  * FOLDED MLP weights stays in net_grad, the table gradient in flat_grad + small_pad. */
 int32_t snb_train_fwd_bwd_lean(const snb_train_ctx *h_ctx, float step_size, float early_stop_eps, float normal_weight,
                                float mask_weight, float eikonal_weight, snb_stream_t stream);
+/* the same iteration with analytic normals (gradient_method = 'ad'): ... -> sdf_fwd_patch -> sdf_grad_patch -> render_fused_ad ->
+ * sdf_bwd_patch (alpha path) -> sdf_grad_bwd_patch (normal / eikonal path).  grad, d_grad: f32 [9 * capacity, 3] scratch. */
+int32_t snb_train_fwd_bwd_lean_ad(const snb_train_ctx *h_ctx, float step_size, float early_stop_eps, float normal_weight,
+                                  float mask_weight, float eikonal_weight, float *grad, float *d_grad, snb_stream_t stream);
 /* Everything between the backward of one iteration and the marcher of the next in ONE launch (exp_runner.py:205-207 +
  * the next iteration's models/fields.py:66-67 weight_norm and dataset_loader.py:223-297 gen_random_patches):
  *   block 0: weight-norm backward net_grad -> (v, g, b, variance) gradients (skipped if grads_unfolded != 0: flat_grad

@@ -480,12 +480,17 @@ __device__ __forceinline__ void pt_weight(Pt &p, float &Tcarry, int lane) {
     p.w = p.alpha * p.T;
 }
 
-template <bool F>
+// AD (gradient_method = 'ad', models/renderer.py:225-226): the per-sample normal is not the directional finite difference but the ANALYTIC
+// gradient of the SDF at the sample start, read from grad_in[(s * 9 + k) * 3 ..] (snb_sdf_grad_patch); the backward then hands
+// d loss / d gradient = w * d loss / d comp_normal + eikonal term to d_grad in the same layout instead of pushing it through V^-1 and the
+// in-patch differences -- d_sdf0 / d_sdf1 carry the alpha path only.
+template <bool F, bool AD>
 __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batch b, const float *__restrict__ net, snb_samples sm,
                                                                   const float *__restrict__ sdf, float normal_w, float mask_w, float eik_w,
                                                                   float *__restrict__ comp, float *__restrict__ wsum,
                                                                   float *__restrict__ d_sdf0, float *__restrict__ d_sdf1,
-                                                                  float *__restrict__ stats) {
+                                                                  float *__restrict__ stats, const float *__restrict__ grad_in,
+                                                                  float *__restrict__ d_grad) {
     __shared__ RenderSmem sh;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int patch = blockIdx.x;
@@ -515,6 +520,11 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
         pt_stage<F>(p, rc, sh, buf, k, lane, valid, base + j0 + lane, S, sm, sdf);
         __syncthreads();
         pt_finish<F>(p, rc, sh, buf, k, lane, valid, inv_s);
+        if (AD) {
+            const float *gi = grad_in + ((int64_t)(base + j0 + lane) * SNB_PATCH + k) * 3;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p.g[a] = valid ? __ldg(gi + a) : 0.f;
+        }
         pt_weight(p, Tc, lane);
         cn[0] += p.w * p.g[0]; cn[1] += p.w * p.g[1]; cn[2] += p.w * p.g[2];
         ws += p.w;
@@ -570,6 +580,11 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
             pt_stage<F>(p, rc, sh, buf, k, lane, valid, s, S, sm, sdf);
             __syncthreads();
             pt_finish<F>(p, rc, sh, buf, k, lane, valid, inv_s);
+            if (AD) {
+                const float *gi = grad_in + ((int64_t)s * SNB_PATCH + k) * 3;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) p.g[a] = valid ? __ldg(gi + a) : 0.f;
+            }
             pt_weight(p, Tc, lane);
         }
         float gw = dc3[0] * p.g[0] + dc3[1] * p.g[1] + dc3[2] * p.g[2] + dws;
@@ -584,7 +599,11 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
 #pragma unroll
         for (int a = 0; a < 3; ++a) dg[a] = p.w * dc3[a] + ek * p.g[a];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) q[a] = rc.vinv[a] * dg[0] + rc.vinv[3 + a] * dg[1] + rc.vinv[6 + a] * dg[2];  // V^T dg
+        for (int a = 0; a < 3; ++a) q[a] = AD ? 0.f : rc.vinv[a] * dg[0] + rc.vinv[3 + a] * dg[1] + rc.vinv[6 + a] * dg[2];  // V^T dg
+        if (AD && valid) {
+            float *go = d_grad + ((int64_t)s * SNB_PATCH + k) * 3;
+            go[0] = dg[0]; go[1] = dg[1]; go[2] = dg[2];
+        }
         float ds0 = 0.f, ds1 = 0.f;
         if (p.raw >= 0.f && p.raw <= 1.f) {   // clip passes the gradient on the closed interval, like torch.clamp
             float ce = p.c + 1e-5f;
@@ -636,8 +655,25 @@ extern "C" int32_t snb_render_fused(const snb_patch_batch *b, const snb_net *net
     if (b->n_patches == 0) return SNB_OK;
     SNB_REQUIRE(sdf && comp && wsum && stats && b->normal_gt && b->mask, SNB_ERR_NULL, "render_fused: null buffer");
     SNB_REQUIRE((d_sdf0 == nullptr) == (d_sdf1 == nullptr), SNB_ERR_NULL, "render_fused: d_sdf0/d_sdf1 must both be given or both be null");
-    render_fused_kernel<true><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
-                                                                                  eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats);
+    render_fused_kernel<true, false><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
+                                                                                         eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats, nullptr, nullptr);
     SNB_LAUNCH_CHECK("render_fused");
+    return SNB_OK;
+}
+
+/* the same stage for gradient_method = 'ad': per-sample normals = grad_in (analytic SDF gradients, f32[9 * capacity, 3] at (s * 9 + k)), seeds
+ * d_grad = d loss / d grad_in in the same layout; d_sdf0 / d_sdf1 carry the alpha path only.  d_sdf0 / d_sdf1 / d_grad all null: forward only. */
+extern "C" int32_t snb_render_fused_ad(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const float *sdf, const float *grad_in,
+                                       float normal_weight, float mask_weight, float eikonal_weight, float *comp, float *wsum,
+                                       float *d_sdf0, float *d_sdf1, float *d_grad, float *stats, snb_stream_t stream) {
+    int32_t rc = check_render(b, net, sm, "render_fused_ad");
+    if (rc) return rc;
+    if (b->n_patches == 0) return SNB_OK;
+    SNB_REQUIRE(sdf && grad_in && comp && wsum && stats && b->normal_gt && b->mask, SNB_ERR_NULL, "render_fused_ad: null buffer");
+    SNB_REQUIRE((d_sdf0 == nullptr) == (d_sdf1 == nullptr) && (d_sdf0 == nullptr) == (d_grad == nullptr), SNB_ERR_NULL,
+                "render_fused_ad: d_sdf0 / d_sdf1 / d_grad must all be given or all be null");
+    render_fused_kernel<true, true><<<(unsigned)b->n_patches, 32 * kRays, 0, S(stream)>>>(*b, net->net, *sm, sdf, normal_weight, mask_weight,
+                                                                                        eikonal_weight, comp, wsum, d_sdf0, d_sdf1, stats, grad_in, d_grad);
+    SNB_LAUNCH_CHECK("render_fused_ad");
     return SNB_OK;
 }

@@ -313,6 +313,213 @@ __global__ void __launch_bounds__(kTile, 3) sdf_bwd_patch_kernel(snb_patch_batch
 }
 
 // ---------------------------------------------------------------------------------------------
+// analytic normals in the fused step (gradient_method = 'ad'; models/renderer.py:225-226, models/fields.py:107-119)
+// ---------------------------------------------------------------------------------------------
+// forward: d sdf / d x at every sample START of every in-patch ray (point p = 9 s + k < 9 S), the one-pass tensor-core evaluator of
+// sdf_eval_grad_kernel on the in-kernel positions of decode_point.  grad: f32 [9 S, 3].
+__global__ void __launch_bounds__(32 * kFwdWarps, 2) sdf_grad_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
+                                                                           float *__restrict__ grad) {
+    extern __shared__ __align__(16) float smem[];
+    const FwdSmem sh = fwd_smem_setup(smem, net.net);
+    float *ts = smem + kMmaSmemFloats(kFwdWarps) + (threadIdx.x >> 5) * 3 * 32 * kTsStride;
+    const LevelCtx *s_lvl = lt.lv;
+    const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
+    const int S = sm.totals[0];
+    const int64_t M = (int64_t)SNB_PATCH * S;
+    const int lane = threadIdx.x & 31;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x; p0 < M; p0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = p0 + threadIdx.x;
+        const bool valid = p < M;
+        PointRef r;
+        r.px = r.py = r.pz = 0.f;
+        if (valid) r = decode_point(p, S, b, sm);
+        float g[3];
+        warp_sdf_grad_mma<true>(valid, r.px, r.py, r.pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, ts, lane, g);
+        if (valid) { grad[3 * p] = g[0]; grad[3 * p + 1] = g[1]; grad[3 * p + 2] = g[2]; }
+    }
+}
+
+// backward of that gradient: given dg = d loss / d (d sdf / d x) per start point, the parameter gradients of
+//     L_g = dg . grad_x sdf = sum_h W1_h s_h u_h,     s = sigmoid(100 z),  z = W0 x_in + b0,  u = W0 r,  r_i = sum_d dg_d d x_in_i / d x_d
+// (r = dg on the three position inputs, dg . grad_x feat_i on a feature input).  With s' = 100 s (1 - s):
+//     dW1_h += s_h u_h
+//     dz_h = W1_h u_h s'_h :   db0 += dz,   dW0 += dz (x) x_in,   d feat_i = sum_h W0[h][i] dz_h      -> table, trilinear VALUE weights
+//     v_h  = W1_h s_h      :   dW0 += v (x) r,                    q_i = sum_h W0[h][i] v_h           -> table, DERIVATIVE weights
+//                                                                 scale * sum_d dg_d (+-1)_d(corner) prod_{e != d} w_e(corner)
+// i.e. the double backward torch.autograd runs for create_graph = True, as two passes of the thread-per-point machinery of
+// sdf_bwd_patch_kernel: the table gets both terms of a corner in one reduction (projections from registers); pass A stages (r, v), pass B
+// stages (x_in, dz), and each pass adds its outer product to the persistent dW0 accumulators.  Thread = point; FMA pipe (this path is not the shipped default; correctness and no host
+// round trip are the point -- the autograd route it replaces takes 25.7 ms per step).
+__global__ void __launch_bounds__(kTile, 1) sdf_grad_bwd_patch_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
+                                                                      const __half2 *__restrict__ feats, const float *__restrict__ d_grad,
+                                                                      float *__restrict__ table_grad, float *__restrict__ net_grad) {
+    extern __shared__ __align__(16) float smem[];
+    float *s_net = smem;                      // kNetFloats
+    float *s_dz = s_net + kNetFloats;         // kTile * kDzStride   (v in pass A, dz in pass B)
+    float *s_x = s_dz + kTile * kDzStride;    // kTile * kXStride    (r in pass A, x_in in pass B)
+    load_net_to_smem(s_net, net.net);
+    const LevelCtx *s_lvl = lt.lv;
+    const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int S = sm.totals[0];
+    const int64_t M = (int64_t)SNB_PATCH * S;
+    const uint32_t n_active = net.n_active, L = feat_row_stride(n_active);
+    const int K = 4 + 2 * (int)n_active;
+    const int grp = tid >> 6, a4 = (tid & 15) * 4, ib = (tid >> 4) & 3;
+    const int n_i = (K - ib + 3) / 4;
+    float accW[9][4];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) accW[i][h] = 0.f;
+    float accW1a = 0.f, accW1b = 0.f;
+
+    auto outer = [&]() {   // dW0T[col][h] += sum_p s_x[p][col] * s_dz[p][h] over this thread's columns (phase B of sdf_bwd_patch_kernel)
+        const float *xg = s_x + (grp * 64) * kXStride + ib;
+        const float *dg_ = s_dz + (grp * 64) * kDzStride + a4;
+        switch (n_i) {
+            case 1: phase_b<1>(accW, xg, dg_); break;
+            case 2: phase_b<2>(accW, xg, dg_); break;
+            case 3: phase_b<3>(accW, xg, dg_); break;
+            case 4: phase_b<4>(accW, xg, dg_); break;
+            case 5: phase_b<5>(accW, xg, dg_); break;
+            case 6: phase_b<6>(accW, xg, dg_); break;
+            case 7: phase_b<7>(accW, xg, dg_); break;
+            case 8: phase_b<8>(accW, xg, dg_); break;
+            default: phase_b<9>(accW, xg, dg_); break;
+        }
+    };
+    for (int64_t tile0 = (int64_t)blockIdx.x * kTile; tile0 < M; tile0 += (int64_t)gridDim.x * kTile) {
+        const int64_t p = tile0 + tid;
+        const bool valid = p < M;
+        PointRef r;
+        r.px = r.py = r.pz = 0.f;
+        float dg[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            r = decode_point(p, S, b, sm);
+            dg[0] = __ldg(d_grad + 3 * p); dg[1] = __ldg(d_grad + 3 * p + 1); dg[2] = __ldg(d_grad + 3 * p + 2);
+        }
+        const bool live = valid && (dg[0] != 0.f || dg[1] != 0.f || dg[2] != 0.f);
+        float *xrow = s_x + tid * kXStride;
+        float4 *dzrow = reinterpret_cast<float4 *>(s_dz + tid * kDzStride);
+        // ---- z (kept features) and u = W0 r, r staged as pass A's input row: [0 | dg | dg . grad feat_l]
+        float z[kH], u[kH];
+#pragma unroll
+        for (int h = 0; h < kH; ++h) u[h] = 0.f;
+        if (valid) {
+            layer0<false, true>(r.px, r.py, r.pz, nullptr, s_lvl, n_active, s_net, const_cast<__half2 *>(feats + p * L), z);
+        } else {
+#pragma unroll
+            for (int h = 0; h < kH; ++h) z[h] = 0.f;
+        }
+        xrow[0] = 0.f; xrow[1] = dg[0]; xrow[2] = dg[1]; xrow[3] = dg[2];
+        rank1_update(u, s_net + kOffW0T + 0 * kH, dg[0]);
+        rank1_update(u, s_net + kOffW0T + 1 * kH, dg[1]);
+        rank1_update(u, s_net + kOffW0T + 2 * kH, dg[2]);
+        for (uint32_t l = 0; l < n_active; ++l) {
+            float rx = 0.f, ry = 0.f;
+            if (live) {
+                const LevelCtx c = s_lvl[l];
+                const Cell cell = cell_of(c, r.px, r.py, r.pz);
+                float2 dv[3];
+                interp_level_grad(c, cell, table, dv);
+                rx = dg[0] * dv[0].x + dg[1] * dv[1].x + dg[2] * dv[2].x;
+                ry = dg[0] * dv[0].y + dg[1] * dv[1].y + dg[2] * dv[2].y;
+            }
+            xrow[4 + 2 * l] = rx;
+            xrow[5 + 2 * l] = ry;
+            rank1_update(u, s_net + kOffW0T + (3 + 2 * l) * kH, rx);
+            rank1_update(u, s_net + kOffW0T + (4 + 2 * l) * kH, ry);
+        }
+        // ---- s, s'; pass A row v = W1 s; dz = W1 u s' kept in u[]; dW1 += s u
+        {
+            float hact[kH];
+#pragma unroll
+            for (int h = 0; h < kH; ++h) {
+                float sp, sg;
+                softplus100_both(z[h], sp, sg);
+                const float w1 = s_net[kOffW1 + h];
+                hact[h] = live ? sg * u[h] : 0.f;
+                z[h] = live ? w1 * sg : 0.f;                                  // v
+                u[h] = live ? w1 * u[h] * 100.f * sg * (1.f - sg) : 0.f;       // dz
+            }
+#pragma unroll
+            for (int q = 0; q < kH / 4; ++q) dzrow[q] = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+            warp_transpose_reduce64(hact, lane);
+            accW1a += hact[0];
+            accW1b += hact[1];
+        }
+        // ---- table: both terms of a corner in ONE reduction -- value weight x d feat (from dz) + derivative weight x q (from v), the two
+        // projections taken straight from the registers
+        if (live) {
+            for (uint32_t l = 0; l < n_active; ++l) {
+                const float4 *w0 = reinterpret_cast<const float4 *>(s_net + kOffW0T + (3 + 2 * l) * kH);
+                const float4 *w1 = w0 + kH / 4;
+                float g0 = 0.f, g1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < kH / 4; ++q) {
+                    const float4 a = w0[q], bq = w1[q];
+                    g0 = fmaf(a.x, u[4 * q], g0); g0 = fmaf(a.y, u[4 * q + 1], g0); g0 = fmaf(a.z, u[4 * q + 2], g0); g0 = fmaf(a.w, u[4 * q + 3], g0);
+                    g1 = fmaf(bq.x, u[4 * q], g1); g1 = fmaf(bq.y, u[4 * q + 1], g1); g1 = fmaf(bq.z, u[4 * q + 2], g1); g1 = fmaf(bq.w, u[4 * q + 3], g1);
+                    q0 = fmaf(a.x, z[4 * q], q0); q0 = fmaf(a.y, z[4 * q + 1], q0); q0 = fmaf(a.z, z[4 * q + 2], q0); q0 = fmaf(a.w, z[4 * q + 3], q0);
+                    q1 = fmaf(bq.x, z[4 * q], q1); q1 = fmaf(bq.y, z[4 * q + 1], q1); q1 = fmaf(bq.z, z[4 * q + 2], q1); q1 = fmaf(bq.w, z[4 * q + 3], q1);
+                }
+                const LevelCtx c = s_lvl[l];
+                const Cell cell = cell_of(c, r.px, r.py, r.pz);
+                float2 *gt = reinterpret_cast<float2 *>(table_grad) + c.offset;
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) {
+                    float wd = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int e0 = (d + 1) % 3, e1 = (d + 2) % 3;
+                        const float a0 = ((k >> e0) & 1u) ? cell.w[e0] : 1.f - cell.w[e0];
+                        const float a1 = ((k >> e1) & 1u) ? cell.w[e1] : 1.f - cell.w[e1];
+                        wd += (((k >> d) & 1u) ? dg[d] : -dg[d]) * a0 * a1;
+                    }
+                    wd *= c.scale;
+                    const float w = corner_weight(cell, k);
+                    atomicAdd(gt + corner_index(c, cell, k), make_float2(fmaf(w, g0, wd * q0), fmaf(w, g1, wd * q1)));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- pass A: dW0 += v (x) r
+        outer();
+        __syncthreads();
+        // ---- pass B: rows x_in and dz;  dW0 += dz (x) x_in (column 0: db0)
+        if (valid) {
+            xrow[0] = 1.f; xrow[1] = r.px; xrow[2] = r.py; xrow[3] = r.pz;
+            for (uint32_t l = 0; l < n_active; ++l) {
+                const float2 f = __half22float2(feats[p * L + l]);
+                xrow[4 + 2 * l] = f.x;
+                xrow[5 + 2 * l] = f.y;
+            }
+        } else {
+            for (int i = 0; i < K; ++i) xrow[i] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < kH / 4; ++q) dzrow[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+        __syncthreads();
+        outer();
+        __syncthreads();
+    }
+
+    // flush: folded-layout gradients
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        int col = ib + 4 * i;
+        if (col < K) {
+            float *dst = (col == 0) ? net_grad + kOffB0 + a4 : net_grad + kOffW0T + (col - 1) * kH + a4;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) atomicAdd(dst + h, accW[i][h]);
+        }
+    }
+    atomicAdd(net_grad + kOffW1 + 2 * lane, accW1a);
+    atomicAdd(net_grad + kOffW1 + 2 * lane + 1, accW1b);
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward with tcgen05 (5th-gen tensor cores, TMEM accumulators)
 // ---------------------------------------------------------------------------------------------
 // CTA = 128 threads = one tile of 128 points; thread t owns point t, and TMEM lane t is row t of every accumulator, so
@@ -1185,4 +1392,43 @@ extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *ne
                                      const float *d_sdf0, const float *d_sdf1, float *table_grad, float *net_grad,
                                      snb_stream_t stream) {
     return snb_sdf_bwd_patch_ws(b, net, sm, feats, d_sdf0, d_sdf1, table_grad, net_grad, nullptr, 0, stream);
+}
+
+/* gradient_method = 'ad': analytic SDF gradient at every sample start of every in-patch ray (points p = 9 s + k < 9 S).  grad: f32 [9 * capacity, 3] */
+extern "C" int32_t snb_sdf_grad_patch(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, float *grad, snb_stream_t stream) {
+    int32_t rc = check_net(net, "sdf_grad_patch");
+    if (rc) return rc;
+    rc = check_patch_args(b, sm, "sdf_grad_patch");
+    if (rc) return rc;
+    SNB_REQUIRE(grad, SNB_ERR_NULL, "sdf_grad_patch: null output");
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sdf_grad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGradSmemBytes);
+        configured = true;
+    }
+    sdf_grad_patch_kernel<<<kNumSMs * 2, 32 * kFwdWarps, kGradSmemBytes, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, grad);
+    SNB_LAUNCH_CHECK("sdf_grad_patch");
+    return SNB_OK;
+}
+
+/* ... and its backward (the double backward of the reference's create_graph = True route): d_grad = d loss / d grad of snb_sdf_grad_patch;
+ * table_grad / net_grad += like snb_sdf_bwd_patch (net_grad w.r.t. the FOLDED weights).  feats: the rows snb_sdf_fwd_patch kept. */
+extern "C" int32_t snb_sdf_grad_bwd_patch(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const void *feats,
+                                          const float *d_grad, float *table_grad, float *net_grad, snb_stream_t stream) {
+    int32_t rc = check_net(net, "sdf_grad_bwd_patch");
+    if (rc) return rc;
+    rc = check_patch_args(b, sm, "sdf_grad_bwd_patch");
+    if (rc) return rc;
+    SNB_REQUIRE(feats && d_grad && table_grad && net_grad, SNB_ERR_NULL, "sdf_grad_bwd_patch: null buffer");
+    SNB_REQUIRE(aligned(table_grad, 8), SNB_ERR_ALIGN, "sdf_grad_bwd_patch: table_grad must be 8-byte aligned");
+    static const size_t smem = sizeof(float) * (kNetFloats + kTile * kDzStride + kTile * kXStride);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(sdf_grad_bwd_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    sdf_grad_bwd_patch_kernel<<<kNumSMs * 3, kTile, smem, S(stream)>>>(*b, *net, make_level_table(net->meta), *sm, (const __half2 *)feats, d_grad,
+                                                                      table_grad, net_grad);
+    SNB_LAUNCH_CHECK("sdf_grad_bwd_patch");
+    return SNB_OK;
 }

@@ -157,6 +157,25 @@ extern "C" int32_t snb_train_fwd_bwd_lean(const snb_train_ctx *c, float step_siz
                                 c->bwd_workspace, c->bwd_workspace_bytes, stream);
 }
 
+extern "C" int32_t snb_train_fwd_bwd_lean_ad(const snb_train_ctx *c, float step_size, float early_stop_eps, float normal_weight, float mask_weight,
+                                             float eikonal_weight, float *grad, float *d_grad, snb_stream_t stream) {
+    SNB_REQUIRE(c, SNB_ERR_NULL, "train_fwd_bwd_lean_ad: null ctx");
+    SNB_REQUIRE(c->flat_param && c->flat_grad && c->net_grad && c->stats && c->sdf && c->feats && c->d_sdf0 && c->d_sdf1 && c->comp && c->wsum && grad && d_grad,
+                SNB_ERR_NULL, "train_fwd_bwd_lean_ad: null buffer");
+    const int n = c->batch.n_patches;
+    int32_t rc;
+    if ((rc = snb_march_visible(&c->batch, &c->net, c->roi, c->res_x, c->res_y, c->res_z, c->grid_binary, step_size, c->jitter, early_stop_eps,
+                                &c->samples, stream))) return rc;
+    if ((rc = snb_compact_samples_stats(n, &c->samples, n * SNB_PATCH, c->batch.mask, c->stats, stream))) return rc;
+    if ((rc = snb_sdf_fwd_patch(&c->batch, &c->net, &c->samples, c->sdf, c->feats, stream))) return rc;
+    if ((rc = snb_sdf_grad_patch(&c->batch, &c->net, &c->samples, grad, stream))) return rc;
+    if ((rc = snb_render_fused_ad(&c->batch, &c->net, &c->samples, c->sdf, grad, normal_weight, mask_weight, eikonal_weight, c->comp, c->wsum,
+                                  c->d_sdf0, c->d_sdf1, d_grad, c->stats, stream))) return rc;
+    if ((rc = snb_sdf_bwd_patch_ws(&c->batch, &c->net, &c->samples, c->feats, c->d_sdf0, c->d_sdf1, c->flat_grad + c->small_pad, c->net_grad,
+                                   c->bwd_workspace, c->bwd_workspace_bytes, stream))) return rc;
+    return snb_sdf_grad_bwd_patch(&c->batch, &c->net, &c->samples, c->feats, d_grad, c->flat_grad + c->small_pad, c->net_grad, stream);
+}
+
 extern "C" int32_t snb_train_optim(const snb_train_ctx *c, float lr, int32_t step_count, float grad_scale, snb_stream_t stream) {
     SNB_REQUIRE(c, SNB_ERR_NULL, "train_optim: null ctx");
     SNB_REQUIRE(c->flat_param && c->flat_grad && c->exp_avg && c->exp_avg_sq, SNB_ERR_NULL, "train_optim: null buffer");

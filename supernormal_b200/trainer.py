@@ -420,11 +420,14 @@ class FusedTrainer:
         self.world_size, self.rank = world_size, rank
         self.n_patches = int(conf["batch_size"])
         assert int(conf["patch_size"]) == 3, "3x3 patches (config/diligent.conf:29)"
-        # 'dfd' (both shipped confs): the fully fused step.  'ad' (models/renderer.py:225-226, SDFNetwork.gradient with create_graph=True):
-        # marching, visibility and Adam stay fused, the render stage runs through the drop-in autograd operators (forward_backward_ad).
+        # 'dfd' (both shipped confs) and 'ad' (models/renderer.py:225-226, SDFNetwork.gradient with create_graph=True) both run fully fused:
+        # 'ad' swaps the render stage for snb_render_fused_ad on analytic gradients (snb_sdf_grad_patch) and adds their double backward
+        # (snb_sdf_grad_bwd_patch).  SNB_AD_FUSED=0 keeps the autograd route (forward_backward_ad: fused marcher / Adam around the drop-in
+        # autograd operators) as the cross-check.
         self.gradient_method = conf.get("gradient_method", "dfd")
         if self.gradient_method not in ("dfd", "ad"):
             raise NotImplementedError(f"gradient_method {self.gradient_method!r}: 'dfd' and 'ad' are implemented ('fd' is a debugging aid of the reference)")
+        self.ad_fused = self.gradient_method == "ad" and os.environ.get("SNB_AD_FUSED", "1") != "0"
         # the kernels hard-wire what both shipped confs select; anything else must fail here, not train silently on other maths
         if conf.get("loss_type", "l1") != "l2":     # exp_runner.py:61 defaults to 'l1' when the key is absent
             raise NotImplementedError(f"fused trainer implements loss_type 'l2' (config/diligent.conf, own_objects.conf); got {conf.get('loss_type', 'l1')!r}")
@@ -434,7 +437,7 @@ class FusedTrainer:
         # (SNB_DP=peer, default) or NCCL allreduce + replicated Adam (SNB_DP=nccl, also the fallback when symmetric memory is unavailable)
         self.peer_mode = False
         self.model = None
-        if world_size > 1 and os.environ.get("SNB_DP", "peer") == "peer" and self.gradient_method == "dfd":
+        if world_size > 1 and os.environ.get("SNB_DP", "peer") == "peer" and (self.gradient_method == "dfd" or self.ad_fused):
             import torch.distributed as dist
             ok = 1
             try:
@@ -457,11 +460,14 @@ class FusedTrainer:
         self.slop = (math.log10(self.start_step) - math.log10(self.end_step)) / conf["end_iter"]
         stride = int(2.0 / self.end_step) + 64
         self.buf = SampleBuffers(self.n_patches, samples_per_ray_cap, stride, self.model.n_levels, self.device)
+        if self.ad_fused:    # analytic gradients of the sample starts and their seeds, f32 [9 * capacity, 3] each
+            self.buf.grad = torch.zeros(P * self.buf.capacity * 3, device=self.device)
+            self.buf.d_grad = torch.zeros(P * self.buf.capacity * 3, device=self.device)
         from .nerfacc_api import OccupancyGrid
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
         self.seed = dp.rank_seed(seed, rank)   # every rank draws its own patches (weak scaling)
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
-        self.lean = (self.peer_mode or os.environ.get("SNB_LEAN", "1") != "0") and self.gradient_method == "dfd"   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
+        self.lean = (self.peer_mode or os.environ.get("SNB_LEAN", "1") != "0") and (self.gradient_method == "dfd" or self.ad_fused)   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
                                       # (snb_train_tail) unfolds, runs Adam, folds the updated weights and pre-samples the next batch
         self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
         self.device_sampler = True    # snb_sample_patches instead of the ATen-op gen_random_patches
@@ -579,7 +585,13 @@ class FusedTrainer:
             m.prep()
             m.net_grad.zero_()
             m.net_stale = False
-        if self.fused_host:
+        if self.fused_host and self.ad_fused and lean:
+            ctx = self._ctx(batch, jitter)
+            call("snb_train_fwd_bwd_lean_ad", C.byref(ctx), float(step_size), 1e-8, float(c["normal_weight"]), float(c["mask_weight"]),
+                 float(c["eikonal_weight"]), ptr(b.grad), ptr(b.d_grad))
+            _lib.LAUNCH_COUNT += 7 - _lib.KERNELS.get("snb_train_fwd_bwd_lean_ad", 1) + (1 if m.n_active > 4 else 0)
+            return
+        if self.fused_host and not self.ad_fused:
             ctx = self._ctx(batch, jitter)
             call("snb_train_fwd_bwd_lean" if lean else "snb_train_fwd_bwd", C.byref(ctx), float(step_size), 1e-8, float(c["normal_weight"]),
                  float(c["mask_weight"]), float(c["eikonal_weight"]))
@@ -606,6 +618,10 @@ class FusedTrainer:
                  ptr(b.dcomp), ptr(b.dwsum))
             call("snb_render_bwd", rb, rn, rs, ptr(b.sdf), ptr(b.comp), ptr(b.wsum), ptr(b.dcomp), ptr(b.dwsum), None,
                  float(c["eikonal_weight"]), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
+        elif self.ad_fused:
+            call("snb_sdf_grad_patch", rb, rn, rs, ptr(b.grad))
+            call("snb_render_fused_ad", rb, rn, rs, ptr(b.sdf), ptr(b.grad), float(c["normal_weight"]), float(c["mask_weight"]),
+                 float(c["eikonal_weight"]), ptr(b.comp), ptr(b.wsum), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.d_grad), ptr(b.stats))
         else:
             call("snb_render_fused", rb, rn, rs, ptr(b.sdf), float(c["normal_weight"]), float(c["mask_weight"]), float(c["eikonal_weight"]),
                  ptr(b.comp), ptr(b.wsum), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
@@ -613,6 +629,8 @@ class FusedTrainer:
             m.net_grad.zero_()
         call("snb_sdf_bwd_patch_ws", rb, rn, rs, ptr(b.feats), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad),
              ptr(b.bwd_ws), b.bwd_ws_bytes)
+        if self.ad_fused:
+            call("snb_sdf_grad_bwd_patch", rb, rn, rs, ptr(b.feats), ptr(b.d_grad), ptr(m.grad[SMALL_PAD:]), ptr(m.net_grad))
         if not lean:
             call("snb_unfold_grads", m.n_levels, ptr(m.small), ptr(m.net_grad), ptr(b.stats), ptr(m.grad))
 
@@ -768,7 +786,7 @@ class FusedTrainer:
             batch = self.sample_batch()
         if jitter is None:
             jitter = torch.rand(self.n_patches, device=self.device, generator=self.gen)
-        if self.gradient_method == "ad":
+        if self.gradient_method == "ad" and not self.ad_fused:
             self.forward_backward_ad(batch, self.step_size(it), jitter)
         else:
             self.forward_backward(batch, self.step_size(it), jitter, lean=self.lean)
