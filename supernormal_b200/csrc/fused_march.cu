@@ -79,7 +79,7 @@ __device__ __forceinline__ float cta_sdf(bool valid, float x, float y, float z, 
     }
     float part = 0.f;
 #pragma unroll
-    for (int i = 0; i < HU; ++i) part = fmaf(s_net[kOffW1 + h0 + i], softplus100<false>(acc[i]), part);
+    for (int i = 0; i < HU; ++i) part = fmaf(s_net[kOffW1 + h0 + i], softplus100(acc[i]), part);
     s_part[warp * 32 + lane] = part;
     __syncthreads();
     float s = s_net[kOffB1];

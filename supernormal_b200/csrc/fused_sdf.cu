@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_eval_kernel(int64_t n, 
         const bool valid = i < n;
         float px = 0.f, py = 0.f, pz = 0.f;
         if (valid) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
-        float s = warp_sdf_mma<false, true>(valid, px, py, pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, nullptr, lane);
+        float s = warp_sdf_mma<false>(valid, px, py, pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, nullptr, lane);
         if (valid) out[i] = mode == 1 ? sigmoidf_(-s * 80.f) : (mode == 2 ? -s : s);
     }
 }
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 2) sdf_eval_grad_kernel(int64_
         float px = 0.f, py = 0.f, pz = 0.f;
         if (valid) { px = __ldg(x + 3 * i); py = __ldg(x + 3 * i + 1); pz = __ldg(x + 3 * i + 2); }
         float g[3];
-        float s = warp_sdf_grad_mma<true>(valid, px, py, pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, ts, lane, g);
+        float s = warp_sdf_grad_mma(valid, px, py, pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, ts, lane, g);
         if (valid) {
             if (sdf) sdf[i] = s;
             grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 4) sdf_fwd_patch_kernel(snb_pa
         PointRef r;
         r.px = r.py = r.pz = 0.f;
         if (valid) r = decode_point(p, S, b, sm);
-        float s = warp_sdf_mma<true, true>(valid, r.px, r.py, r.pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs,
+        float s = warp_sdf_mma<true>(valid, r.px, r.py, r.pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs,
                                            feats + (valid ? p : 0) * L, lane);
         if (valid) sdf[p] = s;
     }
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(32 * kFwdWarps, 2) sdf_grad_patch_kernel(snb_p
         r.px = r.py = r.pz = 0.f;
         if (valid) r = decode_point(p, S, b, sm);
         float g[3];
-        warp_sdf_grad_mma<true>(valid, r.px, r.py, r.pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, ts, lane, g);
+        warp_sdf_grad_mma(valid, r.px, r.py, r.pz, table, s_lvl, net.n_active, sh.net, sh.whi, sh.wlo, sh.xs, ts, lane, g);
         if (valid) { grad[3 * p] = g[0]; grad[3 * p + 1] = g[1]; grad[3 * p + 2] = g[2]; }
     }
 }
@@ -1359,7 +1359,8 @@ extern "C" int32_t snb_sdf_bwd_patch_ws(const snb_patch_batch *b, const snb_net 
     }
     const LevelTable ltab = make_level_table(net->meta);
     const int64_t qcap = sm->capacity + sm->end_capacity;
-    const bool split = use_umma && use_split && net->n_active > 4 && workspace &&
+    static const int split_min = getenv("SNB_BWD_SPLIT_MIN") ? atoi(getenv("SNB_BWD_SPLIT_MIN")) : 5;
+    const bool split = use_umma && use_split && (int)net->n_active >= split_min && workspace &&
                        workspace_bytes >= snb_sdf_bwd_workspace_bytes((int32_t)net->meta.n_levels, sm->capacity, sm->end_capacity);
     if (split) {
         float4 *ws_pos = reinterpret_cast<float4 *>(workspace);

@@ -30,28 +30,15 @@ __device__ __forceinline__ void load_net_to_smem(float *s_net, const float *__re
 }
 
 // softplus(beta=100, threshold=20) and its derivative sigmoid(100 z)   (models/fields.py:70), in the overflow-free form
-// softplus(z) = max(z, 0) + log1p(exp(-|100 z|)) / 100:  one MUFU.EX2 + a polynomial log1p (+ one MUFU.RCP for the derivative).
-// Absolute error of softplus ~2e-9 (the hidden activations are O(0.1)), relative error of the derivative ~2^-21: far below the
-// fp32 noise of the 64-term dot products that consume them.  The XU pipe (16 lanes/clk/SM) is the scarce one in every SDF kernel:
-// 64 softplus per point.  Dropping the MUFU.LG2 took 0.406 -> 0.359 ms per step at iteration 100 (profiles/README.md).
-// Saturation shortcut: for |100 z| >= 17 softplus is max(z, 0) to within log1p(e^-17)/100 = 4e-10 and its derivative is
-// 0 / 1 to within 4e-8, so when every active lane of the warp is saturated (neighbouring points see near-identical
-// pre-activations) the MUFU ops are skipped.
-constexpr float kSoftplusSat = 17.f;
-
-// log(1 + u) on [0, 1], degree-7 minimax fit (max abs error 2.3e-7): with softplus(z) = max(z, 0) + log1p(exp(-|100 z|)) / 100 it
-// replaces the MUFU.LG2 of every softplus by 7 FMAs (the XU pipe issues 4 lanes/clk per scheduler, the FMA pipe 32); the softplus
-// error is 2.3e-9 absolute, far below the fp32 noise of the 64-term dot product that consumes it.
-__device__ __forceinline__ float log1p_poly01(float u) {
-    float p = 0.010243828408420086f;
-    p = fmaf(p, u, -0.053267478942871094f);
-    p = fmaf(p, u, 0.13198965787887573f);
-    p = fmaf(p, u, -0.22396689653396606f);
-    p = fmaf(p, u, 0.327511727809906f);
-    p = fmaf(p, u, -0.4993339478969574f);
-    p = fmaf(p, u, 0.9999702572822571f);
-    return fmaf(p, u, 2.2159764512252877e-07f);
-}
+// softplus(z) = max(z, 0) + log1p(exp(-|100 z|)) / 100 = max(z, 0) + (ln 2 / 100) lg2(1 + u),  u = ex2(-|100 z| / ln 2):
+// MUFU.EX2 + FADD + MUFU.LG2 + FFMA (+ one MUFU.RCP for the derivative).  Absolute error of softplus ~2e-9 (lg2.approx: 2^-22 absolute
+// near 1; the hidden activations are O(0.1)), relative error of the derivative ~2^-21: far below the fp32 noise of the 64-term dot
+// products that consume them.
+// History: round 1 replaced the LG2 by a degree-7 polynomial log1p (7 FMAs) because the XU pipe (16 lanes/clk/SM) was the scarce one
+// in the thread-per-point FMA kernels of the time, and voted per warp to skip saturated units (|100 z| >= 17).  With the .ftz MUFU forms
+// and the tensor-core layer 0 the issue slots are the scarce resource, and the vote never fires on the diligent schedule (exactly 64
+// EX2 per point in every profile, profiles/r02_sass_hist_step_it4800.txt): LG2 without the vote is 3 % of the step faster at
+// iterations 15 / 1000, 1.6 % at 4800 (profiles/r02_softplus_variants.txt).
 
 // MUFU ops as their .ftz PTX forms (see softplus100_both_lg2 below for why)
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -69,15 +56,12 @@ __device__ __forceinline__ float lg2_ftz(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-template <bool SAT = true>
-__device__ __forceinline__ float softplus100(float z) {
-    if (SAT && !__any_sync(__activemask(), fabsf(z) < 0.01f * kSoftplusSat)) return fmaxf(z, 0.f);
-    return fmaf(0.01f, log1p_poly01(ex2_ftz(fabsf(z) * -144.26950408889634f)), fmaxf(z, 0.f));
-}
+__device__ __forceinline__ float softplus100_tail(float u, float z) { return fmaf(0.0069314718056f, lg2_ftz(1.f + u), fmaxf(z, 0.f)); }
+__device__ __forceinline__ float softplus100(float z) { return softplus100_tail(ex2_ftz(fabsf(z) * -144.26950408889634f), z); }
 // softplus and its derivative sigmoid(100 z): one EX2 and one RCP
 __device__ __forceinline__ void softplus100_both(float z, float &sp, float &sg) {
     const float u = ex2_ftz(fabsf(z) * -144.26950408889634f);     // the same u as softplus100: the two forms agree bit for bit on sp
-    sp = fmaf(0.01f, log1p_poly01(u), fmaxf(z, 0.f));
+    sp = softplus100_tail(u, z);
     const float r = rcp_ftz(1.f + u);
     sg = z >= 0.f ? r : u * r;
 }
@@ -139,30 +123,27 @@ __device__ __forceinline__ void layer0(float x, float y, float z, const __half2 
     }
 }
 
-// SAT: softplus saturation shortcut -- pays in the throughput-bound forward kernels; the latency-bound marcher (few warps,
-// one serial chain per ray) keeps the branch-free form.
-template <bool SAT = true>
 __device__ __forceinline__ float layer1(const float (&acc)[kH], const float *s_net) {
     float s = s_net[kOffB1];
     const float4 *w1 = reinterpret_cast<const float4 *>(s_net + kOffW1);
 #pragma unroll
     for (int q = 0; q < kH / 4; ++q) {
         float4 t = w1[q];
-        s = fmaf(t.x, softplus100<SAT>(acc[4 * q + 0]), s);
-        s = fmaf(t.y, softplus100<SAT>(acc[4 * q + 1]), s);
-        s = fmaf(t.z, softplus100<SAT>(acc[4 * q + 2]), s);
-        s = fmaf(t.w, softplus100<SAT>(acc[4 * q + 3]), s);
+        s = fmaf(t.x, softplus100(acc[4 * q + 0]), s);
+        s = fmaf(t.y, softplus100(acc[4 * q + 1]), s);
+        s = fmaf(t.z, softplus100(acc[4 * q + 2]), s);
+        s = fmaf(t.w, softplus100(acc[4 * q + 3]), s);
     }
     return s;
 }
 
-template <bool SAVE_FEAT, bool SAT = true>
+template <bool SAVE_FEAT>
 __device__ __forceinline__ float sdf_point(float x, float y, float z, const __half2 *__restrict__ table,
                                            const LevelCtx *s_lvl, uint32_t n_active, const float *s_net,
                                            __half2 *feat_row) {
     float acc[kH];
     layer0<SAVE_FEAT, false>(x, y, z, table, s_lvl, n_active, s_net, feat_row, acc);
-    return layer1<SAT>(acc, s_net);
+    return layer1(acc, s_net);
 }
 
 // NeuS opacity of an interval from the SDF at its two ends (models/renderer.py:173-179)

@@ -110,41 +110,23 @@ __device__ __forceinline__ void warp_layer0_mma(float (&acc)[2][8][4], const flo
 }
 
 // sdf of the lane's own point from the fragment-layout pre-activations (softplus + layer 1 + row reduction).
-template <bool SAT>
 __device__ __forceinline__ float warp_layer1(const float (&acc)[2][8][4], float *xs, const float *s_net, int lane) {
     const int g = lane >> 2, t = lane & 3;
     float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const float2 w1 = *reinterpret_cast<const float2 *>(s_net + kOffW1 + 8 * nt + 2 * t);
-        // saturation shortcut per group of 8 values (one vote instead of eight): a group that is saturated in every lane is
-        // max(z, 0); otherwise all 8 softplus are evaluated branch-free, back to back, so their MUFU latencies overlap
-        bool sat = SAT;
-        if (SAT) {
-            bool near0 = false;
+        // all 8 softplus of the group branch-free, back to back, so their MUFU latencies overlap
+        float sp[8];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                near0 = near0 || fabsf(100.f * acc[r >> 1][nt][2 * (r & 1)]) < kSoftplusSat || fabsf(100.f * acc[r >> 1][nt][2 * (r & 1) + 1]) < kSoftplusSat;
-            sat = !__any_sync(0xffffffffu, near0);
+        for (int r = 0; r < 4; ++r) {
+            sp[2 * r] = softplus100(acc[r >> 1][nt][2 * (r & 1)]);
+            sp[2 * r + 1] = softplus100(acc[r >> 1][nt][2 * (r & 1) + 1]);
         }
-        if (sat) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                part[r] = fmaf(w1.x, fmaxf(acc[r >> 1][nt][2 * (r & 1)], 0.f), part[r]);
-                part[r] = fmaf(w1.y, fmaxf(acc[r >> 1][nt][2 * (r & 1) + 1], 0.f), part[r]);
-            }
-        } else {
-            float sp[8];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                sp[2 * r] = softplus100<false>(acc[r >> 1][nt][2 * (r & 1)]);
-                sp[2 * r + 1] = softplus100<false>(acc[r >> 1][nt][2 * (r & 1) + 1]);
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                part[r] = fmaf(w1.x, sp[2 * r], part[r]);
-                part[r] = fmaf(w1.y, sp[2 * r + 1], part[r]);
-            }
+        for (int r = 0; r < 4; ++r) {
+            part[r] = fmaf(w1.x, sp[2 * r], part[r]);
+            part[r] = fmaf(w1.y, sp[2 * r + 1], part[r]);
         }
     }
 #pragma unroll
@@ -163,7 +145,7 @@ __device__ __forceinline__ float warp_layer1(const float (&acc)[2][8][4], float 
 
 // Encode the lane's point (gathers + fp16-faithful interpolation), publish it, and evaluate the MLP for the whole warp.
 // All 32 lanes must call this together; lanes without a point pass valid = false (their result is garbage, never NaN-safe).
-template <bool SAVE_FEAT, bool SAT>
+template <bool SAVE_FEAT>
 __device__ __forceinline__ float warp_sdf_mma(bool valid, float x, float y, float z, const __half2 *__restrict__ table,
                                               const LevelCtx *lvl, uint32_t n_active, const float *s_net, const float *s_whi,
                                               const float *s_wlo, float *xs, __half2 *feat_row, int lane) {
@@ -189,7 +171,7 @@ __device__ __forceinline__ float warp_sdf_mma(bool valid, float x, float y, floa
     __syncwarp();
     float acc[2][8][4];
     warp_layer0_mma(acc, xs, s_net, s_whi, s_wlo, ksteps, lane);
-    return warp_layer1<SAT>(acc, xs, s_net, lane);
+    return warp_layer1(acc, xs, s_net, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,7 +183,6 @@ __device__ __forceinline__ float warp_sdf_mma(bool valid, float x, float y, floa
 // (hi*hi, lo*hi, hi*lo) keep the products exact to 2^-22: a single TF32 pass would cost ~5e-4 relative on the normal.
 constexpr int kTsStride = 36;   // floats per point row of a tangent tile (32 feature columns; conflict-free A-fragment loads)
 
-template <bool SAT>
 __device__ __forceinline__ float warp_sdf_grad_mma(bool valid, float x, float y, float z, const __half2 *__restrict__ table,
                                                    const LevelCtx *lvl, uint32_t n_active, const float *s_net, const float *s_whi,
                                                    const float *s_wlo, float *xs, float *ts, int lane, float (&grad)[3]) {
