@@ -88,6 +88,10 @@ __device__ __forceinline__ float cta_sdf(bool valid, float x, float y, float z, 
     return s;
 }
 
+#ifdef SNB_MARCH_DEBUG
+__device__ long long g_march_dbg[8192 * 4];   // per ray: cycles, windows, batches, samples (scripts/march_ray_times.py)
+#endif
+
 template <int W, int MB>
 __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_batch b, snb_net net, LevelTable lt, const float *__restrict__ roi,
                                                                        int3 res, const uint8_t *__restrict__ grid, float step,
@@ -95,14 +99,22 @@ __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_bat
     __shared__ __align__(16) float s_net[kNetFloats];
     __shared__ float s_land[32 * W], s_tm[32 * W];
     __shared__ int s_J[32 * W];
+    __shared__ uint32_t s_hop[2][32 * W + 1];   // pointer doubling over the window's hop chain: end node | (last hop source + 1) << 16
     __shared__ float s_feat[32 * kFeatStride], s_part[32 * W];
-    load_net_to_smem(s_net, net.net);
+#ifdef SNB_MARCH_DEBUG
+    const long long dbg_t0 = clock64();
+    int dbg_windows = 0, dbg_batches = 0;
+#endif
     const LevelCtx *s_lvl = lt.lv;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ray = blockIdx.x;
     if (ray >= b.n_patches) return;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
-    const float inv_s = s_net[kOffInvS];
+    // the MLP weights are staged on the ray's first occupied batch: half to three quarters of a batch's rays never meet an occupied
+    // cell (background patches; per-ray clock64 profile in profiles/r02_march_ray_times.txt) and leave without them
+    bool net_ready = false;
+    float inv_s = 0.f;
+    if (threadIdx.x == 0) s_hop[0][32 * W] = s_hop[1][32 * W] = 32u * W;   // the node behind the window absorbs
     constexpr unsigned kAll = 0xffffffffu;
 
     const RoiCtx rc = make_roi_ctx(roi, res);
@@ -128,6 +140,9 @@ __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_bat
     while (t_mid < far) {
         if (!occ_mode) {
             // ---- speculative window over 32 W points of the empty-space lattice
+#ifdef SNB_MARCH_DEBUG
+            ++dbg_windows;
+#endif
             const int idx = 32 * warp + lane;
             AddChain ch = make_add_chain(t_mid, step);
             float tm;
@@ -146,16 +161,35 @@ __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_bat
             if (inr && !occ) land = march_skip_count_fast(rc, ch, ch.T0 + (uint32_t)idx * ch.Q, tm, step, px, py, pz, d, inv_d, far, J);
             s_land[idx] = land;
             s_tm[idx] = tm;
-            s_J[idx] = !inr ? -1 : (occ ? 0 : J);   // hop length; 0: occupied, -1: beyond far
+            const int hop = !inr ? -1 : (occ ? 0 : J);   // hop length; 0: occupied, -1: beyond far
+            s_J[idx] = hop;
+            // Follow the visited chain 0 -> J(0) -> ... to its first occupied / beyond-far node or out of the window.  With a marching
+            // step near the cell size every hop is 1-3 points long, and walking up to 32 W dependent shared-memory reads serially was
+            // ~60 % of a window (5.7 k cycles per window at iteration 1000).  Pointer doubling instead: node i holds the node reached after
+            // 2^r hops (terminal nodes and the node behind the window absorb) and the source of the last hop made; log2(32 W) rounds of one
+            // shared-memory read each, cut short as soon as node 0's end stops moving.  Same cur / prev as the serial walk.
+            uint32_t e = hop <= 0 ? (uint32_t)idx : (uint32_t)min(idx + hop, 32 * W);
+            uint32_t pv = hop <= 0 ? 0u : (uint32_t)idx + 1u;
+            int hb = 0;
+            s_hop[0][idx] = e | (pv << 16);
             __syncthreads();
-            int cur = 0, prev = -1;
-            bool done = false, found = false;
-            while (cur < 32 * W) {
-                const int c = s_J[cur];
-                if (c <= 0) { done = c < 0; found = c == 0; break; }
-                prev = cur;
-                cur += c;
+            uint32_t v0 = s_hop[0][0];
+#pragma unroll 1
+            for (int r = 1; r < 32 * W; r <<= 1) {
+                const uint32_t v2 = s_hop[hb][e];
+                e = v2 & 0xffffu;
+                if (v2 >> 16) pv = v2 >> 16;
+                hb ^= 1;
+                s_hop[hb][idx] = e | (pv << 16);
+                __syncthreads();
+                const uint32_t v0n = s_hop[hb][0];
+                const bool settled = (v0n & 0xffffu) == (v0 & 0xffffu);
+                v0 = v0n;
+                if (settled) break;
             }
+            const int cur = (int)(v0 & 0xffffu), prev = (int)(v0 >> 16) - 1;
+            const int c_end = cur < 32 * W ? s_J[cur] : 1;
+            const bool done = c_end < 0, found = c_end == 0;
             const float last_land = prev >= 0 ? s_land[prev] : t_mid;
             const float tm_found = found ? s_tm[cur] : 0.f;
             __syncthreads();   // the window arrays are rewritten by the next window
@@ -178,6 +212,14 @@ __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_bat
         }
         // ---- occupied stretch: 31 candidate samples on the lattice t0, t1, t1 (+) dt, ...; candidate 0 is known to be occupied.
         // Every warp holds the same batch: lane i spans [l0, l1] = [t1 after i-1 adds, t1 after i adds] (i = 0: [t0, t1]).
+#ifdef SNB_MARCH_DEBUG
+        ++dbg_batches;
+#endif
+        if (!net_ready) {   // CTA-uniform
+            load_net_to_smem(s_net, net.net);
+            inv_s = s_net[kOffInvS];
+            net_ready = true;
+        }
         float l0 = t0, l1 = t1;
         {
             const AddChain c1 = make_add_chain(t1, step);
@@ -248,6 +290,14 @@ __global__ void __launch_bounds__(32 * W, MB) march_visible_kernel(snb_patch_bat
         sm.counts[ray] = j;
         sm.end_counts[ray] = runs;
         if (overflow) atomicExch(sm.totals + 2, 1);
+#ifdef SNB_MARCH_DEBUG
+        if (ray < 8192) {
+            g_march_dbg[4 * ray] = clock64() - dbg_t0;
+            g_march_dbg[4 * ray + 1] = dbg_windows;
+            g_march_dbg[4 * ray + 2] = dbg_batches;
+            g_march_dbg[4 * ray + 3] = j;
+        }
+#endif
     }
 }
 
@@ -466,6 +516,12 @@ extern "C" int32_t snb_march_visible(const snb_patch_batch *b, const snb_net *ne
     SNB_LAUNCH_CHECK("march_visible");
     return SNB_OK;
 }
+
+#ifdef SNB_MARCH_DEBUG
+extern "C" int32_t snb_debug_march_stats(long long *host_out, int32_t n_rays) {
+    return (int32_t)cudaMemcpyFromSymbol(host_out, g_march_dbg, sizeof(long long) * 4 * (size_t)(n_rays < 8192 ? n_rays : 8192));
+}
+#endif
 
 extern "C" int32_t snb_compact_samples_stats(int32_t n, const snb_samples *sm, int32_t n_mask, const float *mask, float *stats,
                                              snb_stream_t stream) {
