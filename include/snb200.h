@@ -183,6 +183,8 @@ typedef struct snb_samples { /* visible samples on the patch-centre rays, packed
     int32_t *slot_sample;   /* [end_capacity] sample owning each end slot */
     float *scratch_t0;      /* [N, scratch_stride] */
     float *scratch_t1;      /* [N, scratch_stride] */
+    int32_t *launch_order;  /* [N] or NULL: patch indices, most sample chunks first; written by snb_compact_samples(_stats), read by
+                             * snb_render_fused(_ad), whose CTA i then takes patch launch_order[i] (the kernel ends with its longest patch) */
 } snb_samples;
 
 /* Fold weight_norm (models/fields.py:66-67) and the variance network (models/fields.py:133-139,

@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(256) compact_kernel(int32_t n, snb_samples sm)
     const int lane = threadIdx.x & 31;
     const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ray >= n) return;
+    if (sm.launch_order && lane == 0) sm.launch_order[ray] = ray;   // (the one-launch form below sorts; this form is the any-n fallback)
     compact_ray(sm, ray, lane, sm.packed_info[2 * ray], sm.packed_info[2 * ray + 1], sm.end_packed[2 * ray], sm.end_packed[2 * ray + 1]);
 }
 
@@ -420,10 +421,13 @@ __global__ void __launch_bounds__(256) compact_kernel(int32_t n, snb_samples sm)
 // counts of the rays in front of it itself -- n/8 CTAs x n counts from L2 instead of a single-CTA scan kernel and a second launch --
 // and one extra CTA counts the foreground pixels (stats[0]) and zeroes stats[1..7].  Same outputs as scan_counts_kernel + compact_kernel.
 constexpr int kCompactOneMax = 4096;
+constexpr int kOrderBins = 8;   // size classes of the render launch order: 0 samples, 1, 2, ... 6 chunks of 32, more
+__device__ __forceinline__ int order_class(int count) { return count <= 0 ? 0 : min((count + 31) >> 5, kOrderBins - 1); }
 __global__ void __launch_bounds__(256) compact_one_kernel(int32_t n, snb_samples sm, int32_t n_mask, const float *__restrict__ mask,
                                                           float *__restrict__ stats) {
     __shared__ int32_t s_part[2][8];
     __shared__ int32_t s_cnt[2][8];
+    __shared__ int32_t s_hist[2][8][kOrderBins];
     __shared__ float s_m[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_ctas = (n + 7) >> 3;
@@ -456,7 +460,27 @@ __global__ void __launch_bounds__(256) compact_one_kernel(int32_t n, snb_samples
     // ---- sum of the counts in front of this CTA's 8 rays, and the 8 own counts ----
     const int first = blockIdx.x * 8;
     int32_t a0 = 0, a1 = 0;
-    for (int i = threadIdx.x; i < first; i += 256) { a0 += sm.counts[i]; a1 += sm.end_counts[i]; }
+    // launch order of the render stage (longest patches first): rank of a ray = rays in a higher size class (kOrderBins classes by
+    // 32-sample chunks) + rays of its own class in front of it.  Class histograms of ALL rays and of the rays in front of this CTA,
+    // by ballots while the counts stream past; class 0 (no sample: half to three quarters of a batch) follows from the totals.
+    const bool want_order = sm.launch_order != nullptr;
+    int h_all[kOrderBins], h_front[kOrderBins];
+#pragma unroll
+    for (int q = 0; q < kOrderBins; ++q) h_all[q] = h_front[q] = 0;
+    const int i_end = want_order ? n : first;
+    for (int i0 = 0; i0 < i_end; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const int c = i < n ? sm.counts[i] : 0;
+        if (i < first) { a0 += c; a1 += sm.end_counts[i]; }
+        if (want_order) {
+            const int cls = order_class(c);
+#pragma unroll
+            for (int q = 1; q < kOrderBins; ++q) {
+                h_all[q] += __popc(__ballot_sync(0xffffffffu, cls == q));
+                h_front[q] += __popc(__ballot_sync(0xffffffffu, cls == q && i < first));
+            }
+        }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
     const int ray = first + warp;
@@ -464,8 +488,27 @@ __global__ void __launch_bounds__(256) compact_one_kernel(int32_t n, snb_samples
         s_part[0][warp] = a0; s_part[1][warp] = a1;
         s_cnt[0][warp] = ray < n ? sm.counts[ray] : 0;
         s_cnt[1][warp] = ray < n ? sm.end_counts[ray] : 0;
+#pragma unroll
+        for (int q = 1; q < kOrderBins; ++q) { s_hist[0][warp][q] = h_all[q]; s_hist[1][warp][q] = h_front[q]; }
     }
     __syncthreads();
+    if (want_order && lane == 0 && ray < n) {
+        const int mine = order_class(s_cnt[0][warp]);
+        int rank = 0, nonempty_all = 0, nonempty_front = 0;
+#pragma unroll
+        for (int q = 1; q < kOrderBins; ++q) {
+            int all_q = 0, front_q = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { all_q += s_hist[0][w][q]; front_q += s_hist[1][w][q]; }
+            nonempty_all += all_q;
+            nonempty_front += front_q;
+            if (q > mine) rank += all_q;
+            if (q == mine) rank += front_q;
+        }
+        if (mine == 0) rank = nonempty_all + (first - nonempty_front);
+        for (int w = 0; w < warp; ++w) rank += order_class(s_cnt[0][w]) == mine ? 1 : 0;
+        sm.launch_order[rank] = ray;
+    }
     int64_t off[2] = {0, 0};
     int32_t own[2];
 #pragma unroll

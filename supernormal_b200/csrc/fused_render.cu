@@ -493,7 +493,8 @@ __global__ void __launch_bounds__(32 * kRays) render_fused_kernel(snb_patch_batc
                                                                   float *__restrict__ d_grad) {
     __shared__ RenderSmem sh;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int patch = blockIdx.x;
+    // longest patches first when the compaction left a launch order (the kernel ends with its longest patch: up to 13 chunks late in the schedule)
+    const int patch = sm.launch_order ? sm.launch_order[blockIdx.x] : (int)blockIdx.x;
     const float inv_s = __ldg(net + kOffInvS);
     const int S = sm.totals[0];
     const int base = sm.packed_info[2 * patch], n = sm.packed_info[2 * patch + 1];

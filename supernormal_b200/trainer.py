@@ -40,7 +40,7 @@ class SnbSamples(C.Structure):
                 ("counts", C.c_void_p), ("end_counts", C.c_void_p), ("packed_info", C.c_void_p),
                 ("end_packed", C.c_void_p), ("totals", C.c_void_p), ("t0", C.c_void_p), ("t1", C.c_void_p),
                 ("patch_idx", C.c_void_p), ("end_slot", C.c_void_p), ("slot_sample", C.c_void_p),
-                ("scratch_t0", C.c_void_p), ("scratch_t1", C.c_void_p)]
+                ("scratch_t0", C.c_void_p), ("scratch_t1", C.c_void_p), ("launch_order", C.c_void_p)]
 
 
 class SnbDataset(C.Structure):
@@ -257,6 +257,7 @@ class SampleBuffers:
         self.scratch_stride = scratch_stride
         self.scratch_t0 = torch.zeros(n_patches * scratch_stride, **f32)
         self.scratch_t1 = torch.zeros(n_patches * scratch_stride, **f32)
+        self.launch_order = torch.arange(n_patches, **i32)        # patches by sample count, longest first (written by the compaction)
         m_cap = P * (self.capacity + self.end_capacity)
         self.sdf = torch.zeros(m_cap, **f32)
         self.feats = torch.zeros(m_cap * 16 * 2, dtype=torch.float16, device=device)   # rows of feat_row_stride(n_active) <= 16 half2 (fused_sdf.cu)
@@ -271,7 +272,7 @@ class SampleBuffers:
         self.bwd_ws = torch.empty(self.bwd_ws_bytes, dtype=torch.uint8, device=device)
         self._structs = [SnbSamples(self.capacity, self.end_capacity, scratch_stride, *[t.data_ptr() for t in (
             self.counts, self.end_counts, self.packed_info, self.end_packed, st[8:12], self.t0, self.t1,
-            self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1)]) for st in self._sets]
+            self.patch_idx, self.end_slot, self.slot_sample, self.scratch_t0, self.scratch_t1, self.launch_order)]) for st in self._sets]
 
     # the current accumulator set (see __init__)
     @property

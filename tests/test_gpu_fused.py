@@ -597,6 +597,51 @@ def test_single_launch_compaction_equals_scan_then_compact(cuda, cap):
     for k in outs:
         assert torch.equal(got[k], ref[k]), k
     assert b.stats[0].item() == pytest.approx((batch["mask"] > 0.5).sum().item() + 1e-5) and (b.stats[1:] == 0).all()
+    # launch order of the render stage (snb_samples.launch_order): the one-launch form leaves the patches sorted by size class
+    # (chunks of 32 samples, capped at 7; empty patches last), index order within a class; the two-launch form the identity
+    cnt = b.counts.long()                                       # un-clipped marcher counts: what the order is built from
+    cls = torch.where(cnt <= 0, torch.zeros_like(cnt), torch.clamp((cnt + 31) // 32, max=7))
+    want = torch.sort(-cls * (tr.n_patches + 1) + torch.arange(tr.n_patches, device=cuda), stable=True).indices   # class descending, then index
+    assert torch.equal(b.launch_order.long(), want)
+    call("snb_compact_samples", tr.n_patches, rs)
+    assert torch.equal(b.launch_order.long(), torch.arange(tr.n_patches, device=cuda))
+
+
+def test_render_launch_order_changes_no_output(cuda):
+    """snb_render_fused with the launch order left by the compaction (longest patches first) against the identity order: every
+    per-patch / per-sample output is bit-identical (a CTA's work does not depend on which CTA it is); the loss sums meet in atomics."""
+    import ctypes as C
+    from supernormal_b200._lib import call, ptr
+    from supernormal_b200.synthetic import SyntheticDataset, SyntheticScene, DILIGENT_CONF
+    from supernormal_b200.trainer import FusedTrainer, make_batch_struct, SnbSamples
+    ds = SyntheticDataset(SyntheticScene(n_views=6, H=64, W=80, exclude_views=(0,)), device=cuda)
+    tr = FusedTrainer(ds, dict(DILIGENT_CONF, batch_size=301), device=cuda)
+    for _ in range(3):
+        tr.train_step()
+    batch, jitter = tr.sample_batch_device(7)
+    tr.forward_backward(batch, 0.01, jitter, lean=True)   # what train_step runs: march + one-launch compaction (+ order) + forward + render + backward
+    torch.cuda.synchronize()
+    b, c = tr.buf, tr.conf
+    order = b.launch_order.clone()
+    assert not torch.equal(order.long(), torch.arange(tr.n_patches, device=cuda)) and torch.equal(order.long().sort().values, torch.arange(tr.n_patches, device=cuda))
+    bs = make_batch_struct(*[batch[k] for k in ("rays_o", "rays_d", "plane_n", "near", "far", "v_inv", "normal_gt", "mask")])
+    net = tr.model.net_struct()
+    S = int(b.totals[0])
+    outs = {}
+    for name, lo in (("sorted", order), ("identity", None)):
+        st = SnbSamples.from_buffer_copy(b.struct)
+        st.launch_order = lo.data_ptr() if lo is not None else None
+        for t in (b.comp, b.wsum, b.d_sdf0, b.d_sdf1):
+            t.fill_(7.0)
+        b.stats[1:].zero_()
+        call("snb_render_fused", C.byref(bs), C.byref(net), C.byref(st), ptr(b.sdf), float(c["normal_weight"]), float(c["mask_weight"]),
+             float(c["eikonal_weight"]), ptr(b.comp), ptr(b.wsum), ptr(b.d_sdf0), ptr(b.d_sdf1), ptr(b.stats))
+        torch.cuda.synchronize()
+        outs[name] = (b.comp.clone(), b.wsum.clone(), b.d_sdf0[: 9 * S].clone(), b.d_sdf1[: 9 * S].clone(), b.stats.clone())
+    assert S > 500
+    for x, y in zip(outs["sorted"][:4], outs["identity"][:4]):
+        assert torch.equal(x, y)
+    assert torch.allclose(outs["sorted"][4], outs["identity"][4], rtol=1e-5, atol=1e-6)
 
 
 def test_checkpoint_resume_continues_training(cuda):
