@@ -38,6 +38,10 @@ enum snb_status {
 
 const char *snb_last_error(void);
 int32_t snb_version(void);
+/* cudaMemcpyAsync on a caller-chosen stream (kind: 1 host->device, 2 device->host, 3 device->device): the host-fed loop's batch upload
+ * and loss read-back (what Dataset.gen_random_patches(...).cuda() and loss.item() are in exp_runner.py:156-165, 216) without a
+ * framework in between. */
+int32_t snb_copy_async(void *dst, const void *src, int64_t bytes, int32_t kind, snb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Ray marching.  Replaces nerfacc.cuda._C.ray_marching (CS/ray_marching.cu:194-289, bound at

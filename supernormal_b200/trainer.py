@@ -330,6 +330,25 @@ class HostBatchFeeder:
         self.d2h_done = [torch.cuda.Event() for _ in range(2)]
         self.log = torch.zeros(log_capacity, 12, dtype=torch.int32).pin_memory()      # per step: stats[8] (f32 bits) | totals[4]
         self.n_fed = self.n_run = 0
+        # per-step host work is kept to a handful of driver calls (scripts/host_profile_e2e.py: at a 0.19 ms device step the interpreter
+        # is the next bottleneck): field views of every device slot are built once, the copies go through snb_copy_async with cached
+        # raw pointers / stream handles instead of Tensor.copy_ under a stream context manager, and the compute stream object is looked
+        # up again only when torch's current raw stream changes
+        self._slot_batch = [{k_: v for k_, v in self._views(d).items() if k_ != "jitter"} for d in self.dev]
+        self._slot_jitter = [self._views(d)["jitter"] for d in self.dev]
+        self._dev_ptr = [d.data_ptr() for d in self.dev]
+        self._log_ptr, self._log_row_bytes = self.log.data_ptr(), 12 * 4
+        self._set_ptr = [st.data_ptr() for st in tr.buf._sets]
+        self._copy_raw, self._d2h_raw = self.copy_stream.cuda_stream, self.d2h_stream.cuda_stream
+        self._copy_async = _lib.lib().snb_copy_async
+        self._cur, self._cur_raw = None, None
+        self._src_keep = [None] * depth
+
+    def _compute_stream(self) -> "torch.cuda.Stream":
+        raw = _lib.stream()
+        if raw != self._cur_raw:
+            self._cur, self._cur_raw = torch.cuda.current_stream(self.tr.device), raw
+        return self._cur
 
     def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {k: flat[o:o + c].view(shp) for k, (o, c, shp) in self.layout.items()}
@@ -362,28 +381,26 @@ class HostBatchFeeder:
             self.free[slot].synchronize()            # the step that used this slot `depth` submissions ago has finished
         src = batch if torch.is_tensor(batch) else self.pack(batch, jitter, self.host[slot])
         assert src.is_pinned() and src.numel() == self.floats
-        with torch.cuda.stream(self.copy_stream):
-            self.dev[slot].copy_(src, non_blocking=True)
-            self.ready[slot].record(self.copy_stream)
+        self._src_keep[slot] = src                     # the copy is asynchronous: the packed host buffer must outlive it (until the slot's next use)
+        _lib.check(self._copy_async(self._dev_ptr[slot], src.data_ptr(), self.h2d_bytes, 1, self._copy_raw))
+        self.ready[slot].record(self.copy_stream)
         self.n_fed += 1
 
     def step(self) -> None:
         """Run one training iteration on the oldest submitted batch; queue the async read-back of its loss terms."""
         assert self.n_run < self.n_fed, "submit() a batch first"
         tr, slot = self.tr, self.n_run % self.depth
-        cur = torch.cuda.current_stream(tr.device)
+        cur = self._compute_stream()
         cur.wait_event(self.ready[slot])
-        dv = self._views(self.dev[slot])
         tr.buf.flip()                                   # this step accumulates into the set the step before last used ...
         k = tr.buf.set_idx
         cur.wait_event(self.d2h_done[k])                # ... whose read-back (two steps ago) must have left the device
-        tr.train_step(batch={k_: dv[k_] for k_ in BATCH_KEYS}, jitter=dv["jitter"])
+        tr.train_step(batch=self._slot_batch[slot], jitter=self._slot_jitter[slot])
         self.step_done[k].record(cur)
         i = self.n_run % self.log.shape[0]
-        with torch.cuda.stream(self.d2h_stream):        # ONE 48-byte device -> host copy per step, off the compute stream
-            self.d2h_stream.wait_event(self.step_done[k])
-            self.log[i].copy_(tr.buf.stats_totals, non_blocking=True)
-            self.d2h_done[k].record(self.d2h_stream)
+        self.d2h_stream.wait_event(self.step_done[k])   # ONE 48-byte device -> host copy per step, off the compute stream
+        _lib.check(self._copy_async(self._log_ptr + i * self._log_row_bytes, self._set_ptr[k], self._log_row_bytes, 2, self._d2h_raw))
+        self.d2h_done[k].record(self.d2h_stream)
         self.free[slot].record(cur)
         self.n_run += 1
 
@@ -468,6 +485,7 @@ class FusedTrainer:
         self.grid = OccupancyGrid([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], 128).to(self.device)
         self.seed = dp.rank_seed(seed, rank)   # every rank draws its own patches (weak scaling)
         self.fused_host = True        # one C-ABI call per phase instead of one per kernel
+        self._ctx_cache: Dict[tuple, SnbTrainCtx] = {}
         self.lean = (self.peer_mode or os.environ.get("SNB_LEAN", "1") != "0") and (self.gradient_method == "dfd" or self.ad_fused)   # train_step: no prep_net / unfold_grads / sample_patches launches -- the step-tail kernel
                                       # (snb_train_tail) unfolds, runs Adam, folds the updated weights and pre-samples the next batch
         self.legacy_render = False    # per-kernel path only: render_fwd / patch_loss / render_bwd instead of render_fused
@@ -553,6 +571,21 @@ class FusedTrainer:
         return self.own_batch, self.own_jitter
 
     def _ctx(self, batch: dict, jitter) -> SnbTrainCtx:
+        """The fused host calls' argument block.  Rebuilding it is ~35 data_ptr() calls + two ctypes structs, twice per step; every pointer
+        in it is a fixed buffer, so it is cached on what can change between steps: the batch buffers (device-sampler slots / feeder
+        slots), the jitter, the accumulator set (SampleBuffers.flip) and the live level count."""
+        m = self.model
+        key = (batch["rays_o"].data_ptr(), batch["mask"].data_ptr(), 0 if jitter is None else jitter.data_ptr(), self.buf.set_idx,
+               m.n_active, self.grid.binary.data_ptr(), m.flat.data_ptr(), m.grad.data_ptr(), m.table_f16.data_ptr())   # + the buffers a caller may swap
+        hit = self._ctx_cache.get(key)
+        if hit is not None:
+            return hit
+        if len(self._ctx_cache) > 64:
+            self._ctx_cache.clear()
+        ctx = self._ctx_cache[key] = self._build_ctx(batch, jitter)
+        return ctx
+
+    def _build_ctx(self, batch: dict, jitter) -> SnbTrainCtx:
         m, b = self.model, self.buf
         bs = make_batch_struct(batch["rays_o"], batch["rays_d"], batch["plane_n"], batch["near"], batch["far"],
                                batch["v_inv"], batch["normal_gt"], batch["mask"])
@@ -856,6 +889,7 @@ class FusedTrainer:
         grid (rebuilt from the SDF when the checkpoint has none).  The patch stream is counter-based (seed, iteration), so a resumed
         run draws the batches the uninterrupted run would have drawn."""
         m = self.model
+        self._ctx_cache.clear()
         m.load_reference_state_dict(sd)
         m.exp_avg.zero_()
         m.exp_avg_sq.zero_()
