@@ -13,11 +13,78 @@ __global__ void __launch_bounds__(256) sample_patches_kernel(snb_dataset ds, int
 }
 
 // ---- fused occupancy update --------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) occgrid_update_kernel(snb_net net, LevelTable lt, int3 res, const float *__restrict__ roi, int warmup,
+// hidden units per pass of the sweep's MLP and CTAs per SM it is compiled for.  Measured per update at iterations 8 / 1000 / 4800 (1 / 3 / 14
+// live levels; scripts/sweep_time.py): 64 units, 2 CTAs (round 1) 178 / 160 / 339 us; 32, 3: 174 / 149 / 361; 32, 4: 206 / 144 / 376;
+// 16, 4: 167 / 134 / 343 (shipped); 16, 5: 168 / 166 / 605 (spills).
+#ifndef SNB_OCC_CH
+#define SNB_OCC_CH 16
+#endif
+#ifndef SNB_OCC_MINB
+#define SNB_OCC_MINB 4
+#endif
+// SDF of one point with the MLP in passes of CH hidden units: the features of the live levels wait in the thread's own column of a shared
+// tile, so a pass keeps CH accumulators instead of 64 and the kernel fits 3-4 CTAs per SM instead of 2 (the sweep is latency / MIO bound at
+// 16 warps per SM: profiles/r02_sass_hist_occupancy_sweep_warmup.txt).  Same arithmetic per hidden unit as sdf_point, same summation order.
+template <int CH>
+__device__ __forceinline__ float sdf_point_chunked(float x, float y, float z, const __half2 *__restrict__ table, const LevelCtx *s_lvl,
+                                                   uint32_t n_active, const float *s_net, float *s_in) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t l = 0; l < n_active; ++l) {
+        const LevelCtx c = s_lvl[l];
+        Cell cell = cell_of(c, x, y, z);
+        const float2 f = __half22float2(interp_level(c, cell, table));
+        s_in[(2 * l) * nt + tid] = f.x;
+        s_in[(2 * l + 1) * nt + tid] = f.y;
+    }
+    float s = s_net[kOffB1];
+#pragma unroll 1
+    for (int h0 = 0; h0 < kH; h0 += CH) {
+        float acc[CH];
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4 *>(s_net + kOffB0 + h0 + 4 * q);
+            acc[4 * q] = t.x; acc[4 * q + 1] = t.y; acc[4 * q + 2] = t.z; acc[4 * q + 3] = t.w;
+        }
+        const float xin[3] = {x, y, z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4 *>(s_net + kOffW0T + r * kH + h0 + 4 * q);
+                acc[4 * q] = fmaf(w.x, xin[r], acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, xin[r], acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w.z, xin[r], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, xin[r], acc[4 * q + 3]);
+            }
+        }
+        for (uint32_t jf = 0; jf < 2 * n_active; ++jf) {
+            const float v = s_in[jf * nt + tid];
+            const float *wr = s_net + kOffW0T + (3 + jf) * kH + h0;
+#pragma unroll
+            for (int q = 0; q < CH / 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4 *>(wr + 4 * q);
+                acc[4 * q] = fmaf(w.x, v, acc[4 * q]); acc[4 * q + 1] = fmaf(w.y, v, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w.w, v, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4 *>(s_net + kOffW1 + h0 + 4 * q);
+            s = fmaf(t.x, softplus100(acc[4 * q + 0]), s);
+            s = fmaf(t.y, softplus100(acc[4 * q + 1]), s);
+            s = fmaf(t.z, softplus100(acc[4 * q + 2]), s);
+            s = fmaf(t.w, softplus100(acc[4 * q + 3]), s);
+        }
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(256, SNB_OCC_MINB) occgrid_update_kernel(snb_net net, LevelTable lt, int3 res, const float *__restrict__ roi, int warmup,
                                                              float decay, uint64_t seed, uint64_t step, float *__restrict__ occs,
                                                              const float *__restrict__ occs_prev, const uint8_t *__restrict__ binary,
                                                              const unsigned long long *__restrict__ ws) {
     __shared__ __align__(16) float s_net[kNetFloats];
+#if SNB_OCC_CH < 64
+    __shared__ float s_in[2 * SNB_MAX_LEVELS * 256];
+#endif
     load_net_to_smem(s_net, net.net);
     const LevelCtx *s_lvl = lt.lv;
     const __half2 *table = reinterpret_cast<const __half2 *>(net.table_f16);
@@ -55,7 +122,11 @@ __global__ void __launch_bounds__(256, 2) occgrid_update_kernel(snb_net net, Lev
             float lo = __ldg(roi + d), hi = __ldg(roi + 3 + d);
             x[d] = __fmaf_rn(u, __fsub_rn(hi, lo), lo);
         }
+#if SNB_OCC_CH < 64
+        float s = sdf_point_chunked<SNB_OCC_CH>(x[0], x[1], x[2], table, s_lvl, net.n_active, s_net, s_in);
+#else
         float s = sdf_point<false>(x[0], x[1], x[2], table, s_lvl, net.n_active, s_net, nullptr);
+#endif
         occs[c] = fmaxf(__fmul_rn(occs_prev[c], decay), sigmoidf_(-s * 80.f));
     }
 }
