@@ -20,7 +20,7 @@ namespace snb {
 // lattice.  The CTA therefore evaluates 32 W consecutive lattice points at once -- thread k takes the point after
 // k adds (closed form, march_common.cuh), probes the grid and runs the reference's own skip arithmetic as if it
 // were visited -- and then follows the visited chain 0 -> 0+J(0) -> ... through shared memory: the per-voxel
-// dependent load + division chain of the serial marcher becomes one parallel step plus a few ~30-cycle hops, and
+// dependent load + division chain of the serial marcher becomes one parallel step plus log2(32 W) pointer-doubling rounds, and
 // the visited points, hence the emitted samples, are bit-identical.
 //
 // Occupied stretches.  W warps of a CTA own ONE ray.  A lone warp needs ~40 k cycles for the SDF of a 31-sample batch at
