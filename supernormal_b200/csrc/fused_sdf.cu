@@ -548,6 +548,16 @@ struct BwdCfg {
     static constexpr int kMinBlocks = KF <= 8 ? 3 : 2;
 };
 
+// -DSNB_BWD_DEBUG: per-phase clock64 cycles of thread 0 of every CTA, summed over the tiles (scripts/bwd_phase_times.py,
+// profiles/r02_bwd_phase_times.txt).  At 1 live level a 128-point tile costs ~11.5 k cycles: elementwise block 3.9 k, dW0 mma.sync loop
+// 2.7 k, scatter 1.6 k (+2.4 k per further level), issue of the next tile's loads 1.4 k, Z MMA 0.6 k, stage 0.4 k, the three barriers 0.5 k.
+#ifdef SNB_BWD_DEBUG
+__device__ unsigned long long g_bwd_dbg[16];
+#define BWD_T(i) do { if (tid == 0) { const long long _n = clock64(); atomicAdd(&g_bwd_dbg[i], (unsigned long long)(_n - dbg_t)); dbg_t = _n; } } while (0)
+#else
+#define BWD_T(i) do { } while (0)
+#endif
+
 template <int KF>
 __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umma_kernel(snb_patch_batch b, snb_net net, LevelTable lt, snb_samples sm,
                                                                     const __half2 *__restrict__ feats,
@@ -653,6 +663,9 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
     };
     TileRegs nxt;
     fetch((int64_t)blockIdx.x * kTileQ, nxt);
+#ifdef SNB_BWD_DEBUG
+    long long dbg_t = clock64();
+#endif
 
     for (int64_t q0 = (int64_t)blockIdx.x * kTileQ; q0 < Q; q0 += (int64_t)gridDim.x * kTileQ) {
         // ---- stage this thread's point: row tid of X1
@@ -671,11 +684,14 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
             *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, KF, kK1)) = make_float4(xh, yh, zh, xl);
             *reinterpret_cast<float4 *>(a1 + umma::kmajor_off(tid, KF + 4, kK1)) = make_float4(yl, zl, 1.f, 0.f);
         }
+        BWD_T(0);   // stage
         fetch(q0 + (int64_t)gridDim.x * kTileQ, nxt);      // next tile's loads are in flight from here on
+        BWD_T(9);   // issue of the next fetch
         umma::fence_smem_to_async_proxy();
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
+        BWD_T(1);   // barrier 1
 
         // ---- (1) Z = X1 B1^T
         if (tid == 0) {
@@ -691,6 +707,7 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
         }
         if (!umma::mbar_wait(&bar_z, phase)) failed = true;
         umma::fence_after_sync();
+        BWD_T(2);   // MMA Z issue + wait
 
         // ---- (2) dz, dW1 / db1
         {
@@ -721,10 +738,12 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
             for (int o = 16; o; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
             accB1 += ds;
         }
+        BWD_T(3);   // elementwise block + transpose-reduce
         umma::fence_smem_to_async_proxy();
         umma::fence_before_sync();
         __syncthreads();
         umma::fence_after_sync();
+        BWD_T(4);   // barrier 2
 
         // ---- (3) U = dz W0feat  (async on the tensor pipe)
         if (tid == 0 && n_active > 0) {
@@ -760,10 +779,12 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
             }
         }
 
+        BWD_T(5);   // MMA U issue + dW0 mma.sync loop
         // ---- scatter d loss / d features (thread-per-point, straight from TMEM)
         if (n_active > 0) {
             if (!umma::mbar_wait(&bar_u, phase)) failed = true;
             umma::fence_after_sync();
+            BWD_T(6);   // wait U
             // The table scatter is bound by the L2 atomic units (~64 red.v2.f32 lanes per clock chip-wide: 67 M of them are the whole
             // 530 us of the FMA kernel at 14 levels), so contributions to the same grid cell are summed in the warp first:
             // segmented inclusive scan over runs of consecutive lanes with the same cell (16 values: 8 corners x 2 features),
@@ -819,10 +840,15 @@ __global__ void __launch_bounds__(128, BwdCfg<KF>::kMinBlocks) sdf_bwd_patch_umm
                 }
             }
         }
+        BWD_T(7);   // scatter
         phase ^= 1u;
         umma::fence_before_sync();
         __syncthreads();          // tiles a1 / a2 and both accumulators are free again
         umma::fence_after_sync();
+        BWD_T(8);   // barrier 3
+#ifdef SNB_BWD_DEBUG
+        if (tid == 0) atomicAdd(&g_bwd_dbg[15], 1ull);
+#endif
     }
 
     // ---- flush
@@ -1388,6 +1414,14 @@ extern "C" int32_t snb_sdf_bwd_patch_ws(const snb_patch_batch *b, const snb_net 
     SNB_LAUNCH_CHECK("sdf_bwd_patch");
     return SNB_OK;
 }
+
+#ifdef SNB_BWD_DEBUG
+extern "C" int32_t snb_debug_bwd_phases(unsigned long long *host_out, int32_t reset) {
+    int32_t rc = (int32_t)cudaMemcpyFromSymbol(host_out, g_bwd_dbg, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_bwd_dbg, z, sizeof(z)); }
+    return rc;
+}
+#endif
 
 extern "C" int32_t snb_sdf_bwd_patch(const snb_patch_batch *b, const snb_net *net, const snb_samples *sm, const void *feats,
                                      const float *d_sdf0, const float *d_sdf1, float *table_grad, float *net_grad,
